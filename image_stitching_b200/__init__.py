@@ -1,0 +1,571 @@
+"""image_stitching_b200 - B200-native compositing path (rotation warp + multi-band blend).
+
+This package is a thin ctypes mirror of the C ABI in include/image_stitching.h (libisb.so, built
+in-tree by image_stitching_b200/build.py with nvcc for sm_100a).  The class and method names follow
+the OpenCV objects the reference drives (image_stitching.cpp:1086-1229) so that code written against
+`cv2.PyRotationWarper`, `cv2.detail_BlocksGainCompensator` and `cv2.detail_MultiBandBlender` reads the
+same here.  There is NO CPU fallback: if libisb.so is missing or no CUDA device is present the calls
+fail loudly.
+
+Arrays may be numpy arrays (host) or torch CUDA tensors (device pointers are used in place).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libisb.so")
+_lib = None
+
+SPHERICAL, CYLINDRICAL = 0, 1
+INTER_NEAREST, INTER_LINEAR = 0, 1
+BORDER_CONSTANT, BORDER_REFLECT = 0, 2
+EULER = {"XYZ": 0, "YXZ": 1, "ZXY": 2, "ZYX": 3, "YZX": 4, "XZY": 5}
+_KIND = {"spherical": SPHERICAL, "cylindrical": CYLINDRICAL, SPHERICAL: SPHERICAL, CYLINDRICAL: CYLINDRICAL}
+
+
+class IsbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"[{code}] {msg}")
+        self.code = code
+
+
+class Camera(C.Structure):
+    """cv::detail::CameraParams (isb_camera)."""
+    _fields_ = [("focal", C.c_double), ("aspect", C.c_double), ("ppx", C.c_double), ("ppy", C.c_double),
+                ("R", C.c_float * 9), ("t", C.c_float * 3)]
+
+    @staticmethod
+    def make(focal, ppx, ppy, R, aspect=1.0, t=(0, 0, 0)):
+        c = Camera()
+        c.focal, c.aspect, c.ppx, c.ppy = float(focal), float(aspect), float(ppx), float(ppy)
+        c.R[:] = [float(v) for v in np.asarray(R, np.float32).reshape(9)]
+        c.t[:] = [float(v) for v in t]
+        return c
+
+    def K(self):
+        out = np.zeros(9, np.float32)
+        lib().isb_camera_K(C.byref(self), out.ctypes.data_as(C.c_void_p))
+        return out.reshape(3, 3)
+
+
+class _Image(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("width", C.c_int), ("height", C.c_int), ("pitch", C.c_size_t)]
+
+
+class _Gain(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("width", C.c_int), ("height", C.c_int)]
+
+
+class _Mask(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("width", C.c_int), ("height", C.c_int), ("pitch", C.c_size_t)]
+
+
+class Config(C.Structure):
+    _fields_ = [("warp_kind", C.c_int), ("warped_image_scale", C.c_float), ("num_bands", C.c_int),
+                ("strip_index", C.c_int), ("strip_count", C.c_int), ("cache_plan", C.c_int), ("reserved", C.c_int * 8)]
+
+
+class _Pano(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("pitch", C.c_size_t), ("mask", C.c_void_p), ("mask_pitch", C.c_size_t),
+                ("data16", C.c_void_p), ("pitch16", C.c_size_t), ("roi_xywh", C.c_int * 4), ("strip_y0", C.c_int),
+                ("strip_y1", C.c_int)]
+
+
+def lib():
+    """Loads libisb.so (building it when nvcc is available and it is missing).  Never falls back."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_SO):
+        from . import build as _build
+        _build.build()
+    L = C.CDLL(_SO)
+    L.isb_last_error.restype = C.c_char_p
+    L.isb_version.restype = C.c_char_p
+    L.isb_launch_count.restype = C.c_longlong
+    L.isb_composer_stage_name.restype = C.c_char_p
+    L.isb_warper_get_scale.restype = C.c_float
+    for f in ("isb_warper_create", "isb_compensator_create", "isb_blender_create", "isb_composer_create"):
+        getattr(L, f).restype = C.c_void_p
+    L.isb_warper_create.argtypes = [C.c_int, C.c_float]
+    L.isb_warper_set_scale.argtypes = [C.c_void_p, C.c_float]
+    L.isb_num_bands_for.argtypes = [C.c_int, C.c_int, C.c_float]
+    L.isb_quat_slerp.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
+    L.isb_quat_from_axis_angle.argtypes = [C.c_void_p, C.c_double, C.c_void_p]
+    for f in ("isb_warper_destroy", "isb_compensator_destroy", "isb_blender_destroy", "isb_composer_destroy"):
+        getattr(L, f).argtypes = [C.c_void_p]
+        getattr(L, f).restype = None
+    _lib = L
+    return L
+
+
+def _chk(rc):
+    if rc != 0:
+        raise IsbError(rc, lib().isb_last_error().decode())
+
+
+def _is_torch(a):
+    return type(a).__module__.startswith("torch")
+
+
+def _ptr(a):
+    """(address, keepalive) of a numpy array or torch tensor."""
+    if a is None:
+        return None, None
+    if _is_torch(a):
+        a = a if a.is_contiguous() else a.contiguous()
+        return a.data_ptr(), a
+    a = np.ascontiguousarray(a)
+    return a.ctypes.data, a
+
+
+def _f32p(a):
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.float32).reshape(-1))
+    return a.ctypes.data_as(C.c_void_p), a
+
+
+def _shape(a):
+    return tuple(int(v) for v in a.shape)
+
+
+def device_count():
+    return int(lib().isb_device_count())
+
+
+def set_stream(cuda_stream_ptr):
+    lib().isb_set_stream(C.c_void_p(int(cuda_stream_ptr) if cuda_stream_ptr else None))
+
+
+def launch_count(reset=False):
+    return int(lib().isb_launch_count(1 if reset else 0))
+
+
+# ---------------------------------------------------------------------------------------------------
+# pose helpers (quaternion.h / euler.h / serializer.cpp mirrors)
+# ---------------------------------------------------------------------------------------------------
+def _d(a, n):
+    a = np.ascontiguousarray(np.asarray(a, np.float64).reshape(-1))
+    assert a.size == n
+    return a
+
+
+def quat_from_rotation_matrix(R):
+    R, q = _d(R, 9), np.zeros(4)
+    lib().isb_quat_from_rotation_matrix(R.ctypes.data_as(C.c_void_p), q.ctypes.data_as(C.c_void_p))
+    return q
+
+
+def quat_to_rotation_matrix(q):
+    q, R = _d(q, 4), np.zeros(9)
+    lib().isb_quat_to_rotation_matrix(q.ctypes.data_as(C.c_void_p), R.ctypes.data_as(C.c_void_p))
+    return R.reshape(3, 3)
+
+
+def quat_from_euler(e, order="XYZ"):
+    e, q = _d(e, 3), np.zeros(4)
+    lib().isb_quat_from_euler(e.ctypes.data_as(C.c_void_p), EULER[order], q.ctypes.data_as(C.c_void_p))
+    return q
+
+
+def quat_from_axis_angle(axis, angle):
+    a, q = _d(axis, 3), np.zeros(4)
+    lib().isb_quat_from_axis_angle(a.ctypes.data_as(C.c_void_p), float(angle), q.ctypes.data_as(C.c_void_p))
+    return q
+
+
+def quat_multiply(a, b):
+    a, b, q = _d(a, 4), _d(b, 4), np.zeros(4)
+    lib().isb_quat_multiply(a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), q.ctypes.data_as(C.c_void_p))
+    return q
+
+
+def quat_slerp(a, b, t):
+    a, b, q = _d(a, 4), _d(b, 4), np.zeros(4)
+    lib().isb_quat_slerp(a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), float(t),
+                         q.ctypes.data_as(C.c_void_p))
+    return q
+
+
+def pose_from_cam_transform(R, is_portrait):
+    R, o = _d(R, 9), np.zeros(9)
+    lib().isb_pose_from_cam_transform(R.ctypes.data_as(C.c_void_p), int(bool(is_portrait)), o.ctypes.data_as(C.c_void_p))
+    return o.reshape(3, 3)
+
+
+def rotationMatrixToEulerAngles(R, order="XYZ"):
+    R, e = _d(R, 9), np.zeros(3)
+    _chk(lib().isb_rotation_matrix_to_euler(R.ctypes.data_as(C.c_void_p), EULER[order], e.ctypes.data_as(C.c_void_p)))
+    return e
+
+
+def eulerAnglesToRotationMatrix(e, order="XYZ"):
+    e, R = _d(e, 3), np.zeros(9)
+    _chk(lib().isb_euler_to_rotation_matrix(e.ctypes.data_as(C.c_void_p), EULER[order], R.ctypes.data_as(C.c_void_p)))
+    return R.reshape(3, 3)
+
+
+def parseMatrixStr(s):
+    out = np.zeros(1024)
+    side = C.c_int(0)
+    _chk(lib().isb_parse_matrix_str(s.encode(), out.ctypes.data_as(C.c_void_p), out.size, C.byref(side)))
+    return out[: side.value ** 2].reshape(side.value, side.value).copy()
+
+
+def serializeMatrix(m):
+    m = np.asarray(m)
+    is32 = m.dtype == np.float32
+    md = np.ascontiguousarray(m, np.float64)
+    rows, cols = (md.shape + (1,))[:2] if md.ndim == 1 else md.shape
+    buf = C.create_string_buffer(64 * md.size + 16)
+    _chk(lib().isb_serialize_matrix(md.ctypes.data_as(C.c_void_p), int(rows), int(cols), int(is32), buf, len(buf)))
+    return buf.value.decode()
+
+
+def deserializeMatrix(s):
+    out = np.zeros(4096, np.float32)
+    r, c = C.c_int(0), C.c_int(0)
+    _chk(lib().isb_deserialize_matrix(s.encode(), out.ctypes.data_as(C.c_void_p), out.size, C.byref(r), C.byref(c)))
+    return out[: r.value * c.value].reshape(r.value, c.value).copy()
+
+
+def serializeCameraParams(cams, path=None):
+    arr = (Camera * len(cams))(*cams)
+    _chk(lib().isb_save_cams(path.encode() if path else None, arr, len(cams)))
+
+
+def deserializeCameraParams(path=None):
+    n = C.c_int(0)
+    _chk(lib().isb_load_cams(path.encode() if path else None, None, 0, C.byref(n)))
+    arr = (Camera * max(n.value, 1))()
+    _chk(lib().isb_load_cams(path.encode() if path else None, arr, n.value, C.byref(n)))
+    return [arr[i] for i in range(n.value)]
+
+
+def serializeIndices(idx, path=None):
+    a = np.ascontiguousarray(idx, np.int32)
+    _chk(lib().isb_save_indices(path.encode() if path else None, a.ctypes.data_as(C.c_void_p), a.size))
+
+
+def deserializeIndices(path=None):
+    n = C.c_int(0)
+    _chk(lib().isb_load_indices(path.encode() if path else None, None, 0, C.byref(n)))
+    a = np.zeros(max(n.value, 1), np.int32)
+    _chk(lib().isb_load_indices(path.encode() if path else None, a.ctypes.data_as(C.c_void_p), a.size, C.byref(n)))
+    return [int(v) for v in a[: n.value]]
+
+
+# ---------------------------------------------------------------------------------------------------
+# cv::detail::RotationWarper
+# ---------------------------------------------------------------------------------------------------
+class RotationWarper:
+    """Mirror of cv2.PyRotationWarper(kind, scale) for 'spherical' and 'cylindrical'."""
+
+    def __init__(self, kind, scale):
+        if kind not in _KIND:
+            raise IsbError(-5, f"unsupported warper type {kind!r}")
+        self._h = C.c_void_p(lib().isb_warper_create(_KIND[kind], float(scale)))
+        if not self._h:
+            raise IsbError(-5, lib().isb_last_error().decode())
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().isb_warper_destroy(self._h)
+            self._h = None
+
+    def getScale(self):
+        return float(lib().isb_warper_get_scale(self._h))
+
+    def setScale(self, s):
+        _chk(lib().isb_warper_set_scale(self._h, float(s)))
+
+    def warpRoi(self, src_size, K, R):
+        Kp, _k = _f32p(K)
+        Rp, _r = _f32p(R)
+        r = (C.c_int * 4)()
+        _chk(lib().isb_warper_warp_roi(self._h, int(src_size[0]), int(src_size[1]), Kp, Rp, r))
+        return tuple(r)
+
+    def warpPoint(self, pt, K, R):
+        Kp, _k = _f32p(K)
+        Rp, _r = _f32p(R)
+        p, _p = _f32p(pt)
+        o = np.zeros(2, np.float32)
+        _chk(lib().isb_warper_warp_point(self._h, p, Kp, Rp, o.ctypes.data_as(C.c_void_p)))
+        return float(o[0]), float(o[1])
+
+    def warpPointBackward(self, pt, K, R):
+        Kp, _k = _f32p(K)
+        Rp, _r = _f32p(R)
+        p, _p = _f32p(pt)
+        o = np.zeros(2, np.float32)
+        _chk(lib().isb_warper_warp_point_backward(self._h, p, Kp, Rp, o.ctypes.data_as(C.c_void_p)))
+        return float(o[0]), float(o[1])
+
+    def buildMaps(self, src_size, K, R):
+        x, y, w, h = self.warpRoi(src_size, K, R)
+        Kp, _k = _f32p(K)
+        Rp, _r = _f32p(R)
+        xm, ym = np.empty((h, w), np.float32), np.empty((h, w), np.float32)
+        r = (C.c_int * 4)()
+        _chk(lib().isb_warper_build_maps(self._h, int(src_size[0]), int(src_size[1]), Kp, Rp,
+                                         xm.ctypes.data_as(C.c_void_p), ym.ctypes.data_as(C.c_void_p),
+                                         C.c_size_t(w * 4), r))
+        return tuple(r), xm, ym
+
+    def warp(self, src, K, R, interp_mode, border_mode):
+        src = np.ascontiguousarray(src, np.uint8)
+        h, w = src.shape[:2]
+        ch = 1 if src.ndim == 2 else src.shape[2]
+        x, y, rw, rh = self.warpRoi((w, h), K, R)
+        dst = np.empty((rh, rw) if src.ndim == 2 else (rh, rw, ch), np.uint8)
+        Kp, _k = _f32p(K)
+        Rp, _r = _f32p(R)
+        c = (C.c_int * 2)()
+        _chk(lib().isb_warper_warp(self._h, src.ctypes.data_as(C.c_void_p), w, h, ch, C.c_size_t(w * ch), Kp, Rp,
+                                   int(interp_mode), int(border_mode), dst.ctypes.data_as(C.c_void_p),
+                                   C.c_size_t(rw * ch), c))
+        return (c[0], c[1]), dst
+
+
+# ---------------------------------------------------------------------------------------------------
+# cv::detail::BlocksGainCompensator (apply side)
+# ---------------------------------------------------------------------------------------------------
+class BlocksGainCompensator:
+    def __init__(self, bl_width=32, bl_height=32, nr_feeds=1):
+        self._h = C.c_void_p(lib().isb_compensator_create(int(bl_width), int(bl_height)))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().isb_compensator_destroy(self._h)
+            self._h = None
+
+    def setMatGains(self, gains):
+        gs = [np.ascontiguousarray(g, np.float32) for g in gains]
+        n = len(gs)
+        ptrs = (C.c_void_p * n)(*[g.ctypes.data for g in gs])
+        gw = (C.c_int * n)(*[g.shape[1] for g in gs])
+        gh = (C.c_int * n)(*[g.shape[0] for g in gs])
+        _chk(lib().isb_compensator_set_mat_gains(self._h, n, ptrs, gw, gh))
+
+    def getMatGain(self, index):
+        gw, gh = C.c_int(0), C.c_int(0)
+        _chk(lib().isb_compensator_get_mat_gain(self._h, int(index), None, 0, C.byref(gw), C.byref(gh)))
+        out = np.zeros((gh.value, gw.value), np.float32)
+        _chk(lib().isb_compensator_get_mat_gain(self._h, int(index), out.ctypes.data_as(C.c_void_p), out.size,
+                                                C.byref(gw), C.byref(gh)))
+        return out
+
+    def apply(self, index, corner, image, mask=None):
+        img = np.ascontiguousarray(image, np.uint8).copy()
+        h, w = img.shape[:2]
+        c = (C.c_int * 2)(int(corner[0]), int(corner[1]))
+        _chk(lib().isb_compensator_apply(self._h, int(index), c, img.ctypes.data_as(C.c_void_p), w, h,
+                                         C.c_size_t(w * 3), None, C.c_size_t(0)))
+        return img
+
+
+def seam_mask_apply(seam_mask, mask_warped):
+    """dilate(seam) -> resize(INTER_LINEAR_EXACT, mask_warped.size) -> & mask_warped (image_stitching.cpp:1169-1171)."""
+    s = np.ascontiguousarray(seam_mask, np.uint8)
+    m = np.ascontiguousarray(mask_warped, np.uint8).copy()
+    _chk(lib().isb_seam_mask_apply(s.ctypes.data_as(C.c_void_p), s.shape[1], s.shape[0], C.c_size_t(s.shape[1]),
+                                   m.ctypes.data_as(C.c_void_p), m.shape[1], m.shape[0], C.c_size_t(m.shape[1])))
+    return m
+
+
+# ---------------------------------------------------------------------------------------------------
+# cv::detail::MultiBandBlender
+# ---------------------------------------------------------------------------------------------------
+def resultRoi(corners, sizes):
+    c = np.ascontiguousarray(corners, np.int32).reshape(-1, 2)
+    s = np.ascontiguousarray(sizes, np.int32).reshape(-1, 2)
+    r = (C.c_int * 4)()
+    _chk(lib().isb_result_roi(c.ctypes.data_as(C.c_void_p), s.ctypes.data_as(C.c_void_p), len(c), r))
+    return tuple(r)
+
+
+def num_bands_for(dst_w, dst_h, blend_strength=5.0):
+    return int(lib().isb_num_bands_for(int(dst_w), int(dst_h), float(blend_strength)))
+
+
+class MultiBandBlender:
+    def __init__(self, try_gpu=0, num_bands=5):
+        self._h = C.c_void_p(lib().isb_blender_create(int(num_bands)))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().isb_blender_destroy(self._h)
+            self._h = None
+
+    def setNumBands(self, nb):
+        _chk(lib().isb_blender_set_num_bands(self._h, int(nb)))
+
+    def numBands(self):
+        return int(lib().isb_blender_num_bands(self._h))
+
+    def actualNumBands(self):
+        return int(lib().isb_blender_actual_num_bands(self._h))
+
+    def prepare(self, *args):
+        if len(args) == 1:
+            r = (C.c_int * 4)(*[int(v) for v in args[0]])
+            _chk(lib().isb_blender_prepare_roi(self._h, r))
+        else:
+            c = np.ascontiguousarray(args[0], np.int32).reshape(-1, 2)
+            s = np.ascontiguousarray(args[1], np.int32).reshape(-1, 2)
+            _chk(lib().isb_blender_prepare(self._h, c.ctypes.data_as(C.c_void_p), s.ctypes.data_as(C.c_void_p), len(c)))
+
+    def rois(self):
+        a, b = (C.c_int * 4)(), (C.c_int * 4)()
+        _chk(lib().isb_blender_get_rois(self._h, a, b))
+        return tuple(a), tuple(b)
+
+    def tile_rect(self, w, h, tl):
+        r = (C.c_int * 4)()
+        _chk(lib().isb_blender_tile_rect(self._h, int(w), int(h), int(tl[0]), int(tl[1]), r))
+        return tuple(r)
+
+    def feed(self, img, mask, tl):
+        if not _is_torch(img) and np.asarray(img).dtype != np.int16:
+            raise IsbError(-215, "Assertion failed: img.type() == CV_16SC3")
+        if not _is_torch(mask) and np.asarray(mask).dtype != np.uint8:
+            raise IsbError(-215, "Assertion failed: mask.type() == CV_8U")
+        ip, _i = _ptr(img)
+        mp, _m = _ptr(mask)
+        h, w = _shape(mask)[:2]
+        _chk(lib().isb_blender_feed(self._h, C.c_void_p(ip), C.c_size_t(w * 6), C.c_void_p(mp), C.c_size_t(w), w, h,
+                                    int(tl[0]), int(tl[1])))
+
+    def blend(self, dst=None, dst_mask=None):
+        _, rf = self.rois()
+        out = np.empty((rf[3], rf[2], 3), np.int16)
+        m = np.empty((rf[3], rf[2]), np.uint8)
+        _chk(lib().isb_blender_blend(self._h, out.ctypes.data_as(C.c_void_p), C.c_size_t(rf[2] * 6),
+                                     m.ctypes.data_as(C.c_void_p), C.c_size_t(rf[2])))
+        return out, m
+
+
+# ---------------------------------------------------------------------------------------------------
+# fused loop
+# ---------------------------------------------------------------------------------------------------
+def cameras_from_KR(Ks, Rs):
+    """isb_camera list from float32 K = [[f,0,cx],[0,f*a,cy],[0,0,1]] and R."""
+    cams = []
+    for K, R in zip(Ks, Rs):
+        K = np.asarray(K, np.float64)
+        cams.append(Camera.make(K[0, 0], K[0, 2], K[1, 2], R, aspect=K[1, 1] / K[0, 0]))
+    return cams
+
+
+class Composer:
+    """The whole compositing loop on the GPU (isb_composer_*)."""
+
+    def __init__(self, warp="spherical", scale=1.0, num_bands=5, strip_index=0, strip_count=1, cache_plan=True):
+        self.cfg = Config()
+        self.cfg.warp_kind = _KIND[warp]
+        self.cfg.warped_image_scale = float(scale)
+        self.cfg.num_bands = int(num_bands)
+        self.cfg.strip_index, self.cfg.strip_count = int(strip_index), int(strip_count)
+        self.cfg.cache_plan = int(bool(cache_plan))
+        self._h = C.c_void_p(lib().isb_composer_create(C.byref(self.cfg)))
+        self.n = 0
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().isb_composer_destroy(self._h)
+            self._h = None
+
+    def plan(self, cams, src_sizes_wh):
+        n = len(cams)
+        arr = (Camera * n)(*cams)
+        sz = np.ascontiguousarray(src_sizes_wh, np.int32).reshape(n, 2)
+        corners, sizes = np.zeros((n, 2), np.int32), np.zeros((n, 2), np.int32)
+        roi = (C.c_int * 4)()
+        _chk(lib().isb_composer_plan(self._h, arr, sz.ctypes.data_as(C.c_void_p), n, corners.ctypes.data_as(C.c_void_p),
+                                     sizes.ctypes.data_as(C.c_void_p), roi))
+        self.n = n
+        self.corners = [tuple(int(v) for v in c) for c in corners]
+        self.sizes = [tuple(int(v) for v in s) for s in sizes]
+        self.dst_roi = tuple(roi)
+        return self.corners, self.sizes, self.dst_roi
+
+    def run(self, images, gains=None, seam_masks=None, out=None, out_mask=None, out16=None, want16=False):
+        """images: list of HxWx3 uint8 (numpy or torch.cuda).  Outputs are allocated (numpy) unless given."""
+        n = self.n
+        keep = []
+        ia = (_Image * n)()
+        for i, im in enumerate(images):
+            p, k = _ptr(im)
+            keep.append(k)
+            h, w = _shape(im)[:2]
+            ia[i] = _Image(p, w, h, w * 3)
+        ga = None
+        if gains is not None:
+            ga = (_Gain * n)()
+            for i, g in enumerate(gains):
+                if g is None:
+                    ga[i] = _Gain(None, 0, 0)
+                    continue
+                if not _is_torch(g):
+                    g = np.ascontiguousarray(g, np.float32)
+                p, k = _ptr(g)
+                keep.append(k)
+                ga[i] = _Gain(p, _shape(g)[1], _shape(g)[0])
+        sa = None
+        if seam_masks is not None:
+            sa = (_Mask * n)()
+            for i, m in enumerate(seam_masks):
+                if m is None:
+                    sa[i] = _Mask(None, 0, 0, 0)
+                    continue
+                p, k = _ptr(m)
+                keep.append(k)
+                sa[i] = _Mask(p, _shape(m)[1], _shape(m)[0], _shape(m)[1])
+        x, y, w, h = self.dst_roi
+        if out is None:
+            out = np.zeros((h, w, 3), np.uint8)
+        if out_mask is None:
+            out_mask = np.zeros((h, w), np.uint8)
+        if out16 is None and want16:
+            out16 = np.zeros((h, w, 3), np.int16)
+        pano = _Pano()
+        pano.data, k1 = _ptr(out)
+        pano.pitch = w * 3
+        pano.mask, k2 = _ptr(out_mask)
+        pano.mask_pitch = w
+        if out16 is not None:
+            pano.data16, k3 = _ptr(out16)
+            pano.pitch16 = w * 6
+        _chk(lib().isb_composer_run(self._h, ia, ga, sa, n, C.byref(pano)))
+        self.strip_rows = (pano.strip_y0, pano.strip_y1)
+        return dict(result8=out, mask=out_mask, result16=out16, dst_roi=tuple(pano.roi_xywh),
+                    strip_rows=self.strip_rows, corners=self.corners, sizes=self.sizes)
+
+    def timings(self):
+        ms = (C.c_float * 8)()
+        n = lib().isb_composer_last_timings(self._h, ms, 8)
+        if n < 0:
+            _chk(n)
+        return {lib().isb_composer_stage_name(i).decode(): float(ms[i]) for i in range(n)}
+
+    def byte_model(self):
+        S, M, A, B = C.c_double(0), C.c_double(0), C.c_double(0), C.c_double(0)
+        _chk(lib().isb_composer_byte_model(self._h, C.byref(S), C.byref(M), C.byref(A), C.byref(B)))
+        return dict(S=S.value, M=M.value, Ap=A.value, B_alg=B.value)
+
+
+def compose(images, Ks, Rs, scale, warp, num_bands, gains=None, seam_masks=None, want16=True, **kw):
+    """One-shot fused loop with the same result dict as the oracle's compose()."""
+    c = Composer(warp, scale, num_bands, **kw)
+    c.plan(cameras_from_KR(Ks, Rs), [(_shape(im)[1], _shape(im)[0]) for im in images])
+    return c.run(images, gains, seam_masks, want16=want16)
+
+
+def strip_rows(padded_h, final_h, num_bands, index, count):
+    a, b = C.c_int(0), C.c_int(0)
+    _chk(lib().isb_strip_rows(int(padded_h), int(final_h), int(num_bands), int(index), int(count), C.byref(a), C.byref(b)))
+    return a.value, b.value

@@ -1,0 +1,70 @@
+// device_types.hpp - plain structs shared by the host planner and the CUDA kernels.
+#pragma once
+#include <cstdint>
+
+namespace isb {
+
+constexpr int kMaxLevels = 16;  // pyramid levels 0..nb, nb <= 15
+
+struct F2 { float a, b; };
+struct LinCoefDev { int ofs; float frac; };
+
+// One source image + everything the fused warp needs to evaluate, at any ROI pixel, the value the
+// reference's  warp -> mask warp -> compensator.apply -> convertTo(16S) -> seam & mask  chain produces
+// (image_stitching.cpp:1154-1171), without stored xmap/ymap.
+struct ImageDev {
+    const uint8_t* src;   // 8UC3 interleaved (or 8UC1 for mask warps)
+    long long spitch;     // bytes
+    int sw, sh;           // source size
+    int roi_w, roi_h;     // warped size (warpRoi)
+    float kr[9];          // k_rinv = K * R^T
+    const F2* col;        // [roi_w] (sin u', cos u')
+    const F2* row;        // [roi_h] (sin(pi - v'), cos(pi - v')) | (1, v')
+    const float* gain;    // gain grid gh x gw (nullptr: no gain)
+    int gw, gh;
+    const LinCoefDev* gx; // [roi_w]
+    const LinCoefDev* gy; // [roi_h]
+    const uint8_t* seam;  // dilated low-res seam mask mh x mw, tight pitch (nullptr: all 255)
+    int mw, mh;
+    const uint32_t* mx;   // [roi_w] (ofs << 16) | alpha
+    const uint32_t* my;   // [roi_h]
+};
+
+// One pyramid-building unit: a rectangle of the padded panorama (aligned to the 2^nb grid) on which one
+// image's Gaussian (16S x3 planar) and weight (f32) pyramids live.  Level l has size (w >> l, h >> l).
+struct TileDev {
+    int x0, y0, w, h;        // level-0 rect, relative to the padded dst_roi_ origin
+    int img;                 // index into ImageDev[] (fused path) or -1 (classic feed)
+    int left, top;           // ROI top-left relative to the tile origin (copyMakeBorder's left/top)
+    int roi_w, roi_h;        // warped image size (tile px outside are REFLECT padding, weight 0)
+    int16_t* G[kMaxLevels];  // plane p at G[l] + p * gplane[l]
+    float* W[kMaxLevels];
+    int gpitch[kMaxLevels];  // elements
+    int wpitch[kMaxLevels];
+    long long gplane[kMaxLevels];
+};
+
+// A CTA-sized piece of work: block (bx, by) of tile `tile` at the kernel's level.
+struct WorkItem { int tile, bx, by, pad; };
+
+// Destination state of one blend (MultiBandBlender::prepare)
+struct DstDev {
+    int nb;
+    int pw, ph;                // padded level-0 size
+    int fw, fh;                // final (unpadded) size
+    int16_t* C[kMaxLevels];    // collapsed Laplacian levels 1..nb, planar x3
+    int cpitch[kMaxLevels];
+    long long cplane[kMaxLevels];
+    int cells_x, cells_y;      // macro cells of 2^nb x 2^nb level-0 px
+    const int* cell_start;     // CSR: tiles covering each macro cell, ascending feed order
+    const int* cell_tiles;
+    int row0, row1;            // level-0 rows [row0,row1) this process owns (strip)
+};
+
+struct OutDev {
+    uint8_t* out8; long long pitch8;     // 8UC3 interleaved, may be null
+    uint8_t* mask; long long mpitch;     // 8UC1, may be null
+    int16_t* out16; long long pitch16;   // 16SC3 interleaved (bytes pitch), may be null
+};
+
+}  // namespace isb

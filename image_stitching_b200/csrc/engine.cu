@@ -1,0 +1,876 @@
+// engine.cu - host side of the device pipeline (memory, planning, launches).
+#include "engine.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <thread>
+
+#include "kernels.cuh"
+
+namespace isb {
+
+// ------------------------------------------------------------------------------------------------
+// plumbing
+// ------------------------------------------------------------------------------------------------
+void cuda_check(cudaError_t e, const char* what)
+{
+    if (e == cudaSuccess) return;
+    cudaGetLastError();  // clear the sticky-free error state
+    throw Error(e == cudaErrorMemoryAllocation ? ISB_ERR_NO_MEM : ISB_ERR_GPU_API,
+                std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+static thread_local cudaStream_t t_stream = nullptr;
+cudaStream_t current_stream() { return t_stream; }
+void set_current_stream(cudaStream_t s) { t_stream = s; }
+
+void require_device()
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        throw Error(ISB_ERR_GPU_API,
+                    "no CUDA device available: image_stitching_b200 has no CPU fallback (the compositing path runs "
+                    "only as sm_100a kernels)");
+    }
+}
+
+MemKind mem_kind(const void* p)
+{
+    cudaPointerAttributes a{};
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return MemKind::Host;
+    }
+    if (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) return MemKind::Device;
+    if (a.type == cudaMemoryTypeHost) return MemKind::HostPinned;
+    return MemKind::Host;
+}
+
+DevBuf::~DevBuf()
+{
+    if (p_) cudaFree(p_);
+}
+void* DevBuf::ensure(size_t bytes)
+{
+    if (bytes <= cap_ && p_) return p_;
+    if (p_) {
+        ISB_CUDA(cudaFree(p_));  // synchronises with in-flight work that may still read the old block
+        p_ = nullptr;
+        cap_ = 0;
+    }
+    size_t want = std::max<size_t>(bytes, 256);
+    ISB_CUDA(cudaMalloc(&p_, want));
+    cap_ = want;
+    return p_;
+}
+
+PinBuf::~PinBuf()
+{
+    if (p_) cudaFreeHost(p_);
+}
+void* PinBuf::ensure(size_t bytes)
+{
+    if (bytes <= cap_ && p_) return p_;
+    if (p_) {
+        ISB_CUDA(cudaFreeHost(p_));
+        p_ = nullptr;
+        cap_ = 0;
+    }
+    ISB_CUDA(cudaMallocHost(&p_, std::max<size_t>(bytes, 256)));
+    cap_ = std::max<size_t>(bytes, 256);
+    return p_;
+}
+
+// copy a (rows x row_bytes) block between any two memory kinds on `st`
+static void copy2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t row_bytes, size_t rows,
+                   cudaStream_t st)
+{
+    if (rows == 0 || row_bytes == 0) return;
+    if (dpitch == row_bytes && spitch == row_bytes)
+        ISB_CUDA(cudaMemcpyAsync(dst, src, row_bytes * rows, cudaMemcpyDefault, st));
+    else
+        ISB_CUDA(cudaMemcpy2DAsync(dst, dpitch, src, spitch, row_bytes, rows, cudaMemcpyDefault, st));
+}
+
+static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// ------------------------------------------------------------------------------------------------
+// PyramidEngine
+// ------------------------------------------------------------------------------------------------
+PyramidEngine::~PyramidEngine()
+{
+    for (DevBuf* b : extra_) delete b;
+}
+
+void PyramidEngine::reset(const BlendGeometry& g, int sub_y0, int sub_h, int own_y0, int own_y1)
+{
+    g_ = g;
+    sub_y0_ = sub_y0;
+    sub_h_ = sub_h;
+    own_y0_ = own_y0;
+    own_y1_ = own_y1;
+    tiles_.clear();
+    tile_off_.clear();
+    committed_ = 0;
+    arena_.begin();
+    frozen_arena_ = false;
+    warp_work_.clear();
+    down_work_.assign(g.nb, {});
+    ISB_ASSERT(g.nb < kMaxLevels);
+}
+
+int PyramidEngine::add_tile(int img_index, int w, int h, int tlx, int tly)
+{
+    int tl[2], br[2];
+    g_.tile_rect(w, h, tlx, tly, tl, br);
+    const int X0 = tl[0] - g_.roi.x, X1 = br[0] - g_.roi.x;
+    const int Y0 = tl[1] - g_.roi.y, Y1 = br[1] - g_.roi.y;
+    const int cy0 = std::max(Y0, sub_y0_), cy1 = std::min(Y1, sub_y0_ + sub_h_);
+    if (cy1 <= cy0 || X1 <= X0) return -1;
+    TileDev t{};
+    t.x0 = X0;
+    t.y0 = cy0 - sub_y0_;
+    t.w = X1 - X0;
+    t.h = cy1 - cy0;
+    t.img = img_index;
+    t.left = tlx - tl[0];
+    t.top = (tly - g_.roi.y) - cy0;
+    t.roi_w = w;
+    t.roi_h = h;
+    tiles_.push_back(t);
+    return (int)tiles_.size() - 1;
+}
+
+void PyramidEngine::commit_tiles(cudaStream_t st)
+{
+    const int first = committed_, end = (int)tiles_.size();
+    if (first == end) return;
+    const int nb = g_.nb;
+    // storage layout of the new tiles
+    Arena local;
+    Arena& ar = (first == 0) ? arena_ : local;
+    ar.begin();
+    std::vector<size_t> goff((size_t)(end - first) * (nb + 1)), woff(goff.size());
+    for (int t = first; t < end; ++t) {
+        TileDev& T = tiles_[t];
+        for (int l = 0; l <= nb; ++l) {
+            const int wl = T.w >> l, hl = T.h >> l;
+            T.gpitch[l] = round_up(wl, 8);
+            T.wpitch[l] = round_up(wl, 4);
+            T.gplane[l] = (long long)T.gpitch[l] * hl;
+            goff[(size_t)(t - first) * (nb + 1) + l] = ar.take((size_t)T.gplane[l] * 3 * sizeof(int16_t));
+            woff[(size_t)(t - first) * (nb + 1) + l] = ar.take((size_t)T.wpitch[l] * hl * sizeof(float));
+        }
+    }
+    char* base;
+    if (first == 0) base = arena_.commit();
+    else {
+        DevBuf* b = new DevBuf();
+        extra_.push_back(b);
+        base = static_cast<char*>(b->ensure(local.used()));
+    }
+    for (int t = first; t < end; ++t)
+        for (int l = 0; l <= nb; ++l) {
+            tiles_[t].G[l] = reinterpret_cast<int16_t*>(base + goff[(size_t)(t - first) * (nb + 1) + l]);
+            tiles_[t].W[l] = reinterpret_cast<float*>(base + woff[(size_t)(t - first) * (nb + 1) + l]);
+        }
+    // work lists for the new tiles
+    warp_work_.clear();
+    for (auto& v : down_work_) v.clear();
+    for (int t = first; t < end; ++t) {
+        const TileDev& T = tiles_[t];
+        for (int by = 0; by < (T.h + kWarpBlockH - 1) / kWarpBlockH; ++by)
+            for (int bx = 0; bx < (T.w + kWarpBlockW - 1) / kWarpBlockW; ++bx) warp_work_.push_back(WorkItem{t, bx, by, 0});
+        for (int l = 0; l < nb; ++l) {
+            const int ow = T.w >> (l + 1), oh = T.h >> (l + 1);
+            for (int by = 0; by < (oh + kDownBlockH - 1) / kDownBlockH; ++by)
+                for (int bx = 0; bx < (ow + kDownBlockW - 1) / kDownBlockW; ++bx)
+                    down_work_[l].push_back(WorkItem{t, bx, by, 0});
+        }
+    }
+    // uploads (pageable sources: the runtime stages them before returning, so the vectors may be reused)
+    TileDev* td = static_cast<TileDev*>(tiles_dev_.ensure(std::max<size_t>(tiles_.size(), 16) * 2 * sizeof(TileDev)));
+    ISB_CUDA(cudaMemcpyAsync(td, tiles_.data(), tiles_.size() * sizeof(TileDev), cudaMemcpyHostToDevice, st));
+    if (!warp_work_.empty()) {
+        void* p = warp_work_dev_.ensure(warp_work_.size() * sizeof(WorkItem));
+        ISB_CUDA(cudaMemcpyAsync(p, warp_work_.data(), warp_work_.size() * sizeof(WorkItem), cudaMemcpyHostToDevice, st));
+    }
+    size_t total = 0;
+    down_off_.assign(nb + 1, 0);
+    for (int l = 0; l < nb; ++l) {
+        down_off_[l] = total;
+        total += down_work_[l].size();
+    }
+    down_off_[nb] = total;
+    if (total) {
+        WorkItem* p = static_cast<WorkItem*>(down_work_dev_.ensure(total * sizeof(WorkItem)));
+        for (int l = 0; l < nb; ++l)
+            if (!down_work_[l].empty())
+                ISB_CUDA(cudaMemcpyAsync(p + down_off_[l], down_work_[l].data(), down_work_[l].size() * sizeof(WorkItem),
+                                         cudaMemcpyHostToDevice, st));
+    }
+    committed_ = end;
+    dst_.cell_start = nullptr;  // CSR must be rebuilt
+}
+
+void PyramidEngine::build_pyramids(int first, int end, cudaStream_t st)
+{
+    (void)first;
+    (void)end;  // the work lists always describe the last committed batch
+    const WorkItem* base = down_work_dev_.as<WorkItem>();
+    for (int l = 0; l < g_.nb; ++l)
+        launch_pyrdown_tiles(base + down_off_[l], (int)(down_off_[l + 1] - down_off_[l]), tiles_dev(), l, st);
+}
+
+void PyramidEngine::blend(const OutDev& out, cudaStream_t st)
+{
+    const int nb = g_.nb;
+    if (!dst_.cell_start) {
+        // destination pyramid (levels 1..nb) + CSR of covering tiles per macro cell
+        dst_ = DstDev{};
+        dst_.nb = nb;
+        dst_.pw = g_.roi.w;
+        dst_.ph = sub_h_;
+        dst_.fw = g_.roi_final.w;
+        dst_.fh = g_.roi_final.h - sub_y0_;
+        dst_.row0 = own_y0_ - sub_y0_;
+        dst_.row1 = own_y1_ - sub_y0_;
+        dst_.cells_x = dst_.pw >> nb;
+        dst_.cells_y = dst_.ph >> nb;
+        const int ncell = dst_.cells_x * dst_.cells_y;
+        std::vector<int> start(ncell + 1, 0);
+        for (const TileDev& T : tiles_)
+            for (int cy = T.y0 >> nb; cy < (T.y0 + T.h) >> nb; ++cy)
+                for (int cx = T.x0 >> nb; cx < (T.x0 + T.w) >> nb; ++cx) ++start[cy * dst_.cells_x + cx + 1];
+        for (int i = 0; i < ncell; ++i) start[i + 1] += start[i];
+        std::vector<int> fill(start.begin(), start.end() - 1), list(std::max(start[ncell], 1));
+        for (int t = 0; t < (int)tiles_.size(); ++t) {  // ascending t == feed order
+            const TileDev& T = tiles_[t];
+            for (int cy = T.y0 >> nb; cy < (T.y0 + T.h) >> nb; ++cy)
+                for (int cx = T.x0 >> nb; cx < (T.x0 + T.w) >> nb; ++cx) list[fill[cy * dst_.cells_x + cx]++] = t;
+        }
+        size_t cbytes = 0;
+        std::vector<size_t> coff(nb + 1, 0);
+        for (int l = 1; l <= nb; ++l) {
+            dst_.cpitch[l] = round_up(dst_.pw >> l, 8);
+            dst_.cplane[l] = (long long)dst_.cpitch[l] * (dst_.ph >> l);
+            coff[l] = cbytes;
+            cbytes += ((size_t)dst_.cplane[l] * 3 * sizeof(int16_t) + 255) & ~size_t(255);
+        }
+        char* cb = static_cast<char*>(dst_buf_.ensure(std::max<size_t>(cbytes, 256)));
+        for (int l = 1; l <= nb; ++l) dst_.C[l] = reinterpret_cast<int16_t*>(cb + coff[l]);
+        int* cd = static_cast<int*>(cells_dev_.ensure((start.size() + list.size()) * sizeof(int)));
+        ISB_CUDA(cudaMemcpyAsync(cd, start.data(), start.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        ISB_CUDA(cudaMemcpyAsync(cd + start.size(), list.data(), list.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        dst_.cell_start = cd;
+        dst_.cell_tiles = cd + start.size();
+    }
+    for (int l = nb; l >= 0; --l) launch_blend_level(dst_, tiles_dev(), l, out, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Warper
+// ------------------------------------------------------------------------------------------------
+static void check_KR(const float* K, const float* R)
+{
+    if (!K || !R) throw Error(ISB_ERR_NULL_PTR, "K and R must be 3x3 CV_32F matrices (got a null pointer)");
+}
+
+Rect Warper::warp_roi(int sw, int sh, const float* K, const float* R)
+{
+    check_KR(K, R);
+    ISB_ASSERT(sw > 0 && sh > 0);
+    Projector p;
+    p.set(kind_, scale_, K, R);
+    return p.warp_roi(sw, sh);
+}
+
+void Warper::warp_point(const float* pt, const float* K, const float* R, float* out, bool backward)
+{
+    check_KR(K, R);
+    Projector p;
+    p.set(kind_, scale_, K, R);
+    if (backward) p.backward(pt[0], pt[1], out[0], out[1]);
+    else p.forward(pt[0], pt[1], out[0], out[1]);
+}
+
+void Warper::prepare_image(int sw, int sh, const float* K, const float* R, ImageDev& I, Rect& roi, cudaStream_t st)
+{
+    check_KR(K, R);
+    ISB_ASSERT(sw > 0 && sh > 0);
+    Projector p;
+    p.set(kind_, scale_, K, R);
+    roi = p.warp_roi(sw, sh);
+    std::vector<Float2> col, row;
+    build_trig_tables(p, roi, col, row);
+    F2* t = static_cast<F2*>(tab_.ensure((col.size() + row.size()) * sizeof(F2)));
+    ISB_CUDA(cudaMemcpyAsync(t, col.data(), col.size() * sizeof(F2), cudaMemcpyHostToDevice, st));
+    ISB_CUDA(cudaMemcpyAsync(t + col.size(), row.data(), row.size() * sizeof(F2), cudaMemcpyHostToDevice, st));
+    I = ImageDev{};
+    I.sw = sw;
+    I.sh = sh;
+    I.roi_w = roi.w;
+    I.roi_h = roi.h;
+    std::memcpy(I.kr, p.k_rinv, sizeof(I.kr));
+    I.col = t;
+    I.row = t + col.size();
+}
+
+Rect Warper::build_maps(int sw, int sh, const float* K, const float* R, float* xmap, float* ymap, size_t pitch)
+{
+    require_device();
+    cudaStream_t st = current_stream();
+    ImageDev I;
+    Rect roi;
+    prepare_image(sw, sh, K, R, I, roi, st);
+    if (!xmap || !ymap) throw Error(ISB_ERR_NULL_PTR, "xmap/ymap are null");
+    const bool dev = mem_kind(xmap) == MemKind::Device;
+    const size_t row_bytes = (size_t)roi.w * sizeof(float);
+    float *dx = xmap, *dy = ymap;
+    size_t dp = pitch;
+    if (!dev) {
+        dp = round_up((int)row_bytes, 256);
+        dx = static_cast<float*>(xm_.ensure(dp * roi.h));
+        dy = static_cast<float*>(ym_.ensure(dp * roi.h));
+    }
+    launch_build_maps(I, dx, dy, (long long)dp, st);
+    if (!dev) {
+        copy2d(xmap, pitch, dx, dp, row_bytes, roi.h, st);
+        copy2d(ymap, pitch, dy, dp, row_bytes, roi.h, st);
+    }
+    ISB_CUDA(cudaStreamSynchronize(st));
+    return roi;
+}
+
+void Warper::warp(const uint8_t* src, int sw, int sh, int ch, size_t spitch, const float* K, const float* R, int interp,
+                  int border, uint8_t* dst, size_t dpitch, int* corner)
+{
+    require_device();
+    if (!src || !dst) throw Error(ISB_ERR_NULL_PTR, "src/dst are null");
+    ISB_ASSERT(ch == 1 || ch == 3);
+    ISB_ASSERT(interp == ISB_INTER_NEAREST || interp == ISB_INTER_LINEAR);
+    ISB_ASSERT(border == ISB_BORDER_CONSTANT || border == ISB_BORDER_REFLECT);
+    ISB_ASSERT(spitch >= (size_t)sw * ch);
+    cudaStream_t st = current_stream();
+    ImageDev I;
+    Rect roi;
+    prepare_image(sw, sh, K, R, I, roi, st);
+    ISB_ASSERT(dpitch >= (size_t)roi.w * ch);
+    if (mem_kind(src) == MemKind::Device) {
+        I.src = src;
+        I.spitch = (long long)spitch;
+    } else {
+        const size_t sp = (size_t)sw * ch;
+        uint8_t* d = static_cast<uint8_t*>(src_.ensure(sp * sh));
+        copy2d(d, sp, src, spitch, sp, sh, st);
+        I.src = d;
+        I.spitch = (long long)sp;
+    }
+    const bool ddev = mem_kind(dst) == MemKind::Device;
+    uint8_t* dd = dst;
+    size_t dp = dpitch;
+    if (!ddev) {
+        dp = (size_t)roi.w * ch;
+        dd = static_cast<uint8_t*>(dst_.ensure(dp * roi.h));
+    }
+    launch_warp_generic(I, ch, interp, border, dd, (long long)dp, st);
+    if (!ddev) copy2d(dst, dpitch, dd, dp, (size_t)roi.w * ch, roi.h, st);
+    ISB_CUDA(cudaStreamSynchronize(st));
+    if (corner) {
+        corner[0] = roi.x;
+        corner[1] = roi.y;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Compensator / seam mask
+// ------------------------------------------------------------------------------------------------
+void Compensator::set_gains(int n, const float* const* g, const int* gw, const int* gh)
+{
+    gains_.assign(n, {});
+    gw_.assign(gw, gw + n);
+    gh_.assign(gh, gh + n);
+    for (int i = 0; i < n; ++i) {
+        ISB_ASSERT(g[i] != nullptr && gw[i] > 0 && gh[i] > 0);
+        gains_[i].assign(g[i], g[i] + (size_t)gw[i] * gh[i]);
+    }
+}
+
+static void upload_gain_tables(const float* gain, int gw, int gh, int w, int h, DevBuf& aux, const float*& g_dev,
+                               const LinCoefDev*& gx_dev, const LinCoefDev*& gy_dev, cudaStream_t st)
+{
+    std::vector<LinCoef> gx, gy;
+    build_linear_f32_table(gw, w, true, gx);
+    build_linear_f32_table(gh, h, false, gy);
+    const size_t gbytes = ((size_t)gw * gh * sizeof(float) + 15) & ~size_t(15);
+    char* base = static_cast<char*>(aux.ensure(gbytes + (gx.size() + gy.size()) * sizeof(LinCoefDev)));
+    ISB_CUDA(cudaMemcpyAsync(base, gain, (size_t)gw * gh * sizeof(float), cudaMemcpyHostToDevice, st));
+    ISB_CUDA(cudaMemcpyAsync(base + gbytes, gx.data(), gx.size() * sizeof(LinCoefDev), cudaMemcpyHostToDevice, st));
+    ISB_CUDA(cudaMemcpyAsync(base + gbytes + gx.size() * sizeof(LinCoefDev), gy.data(), gy.size() * sizeof(LinCoefDev),
+                             cudaMemcpyHostToDevice, st));
+    g_dev = reinterpret_cast<const float*>(base);
+    gx_dev = reinterpret_cast<const LinCoefDev*>(base + gbytes);
+    gy_dev = gx_dev + gx.size();
+}
+
+void Compensator::apply(int index, uint8_t* image, int w, int h, size_t pitch)
+{
+    require_device();
+    if (!image) throw Error(ISB_ERR_NULL_PTR, "image is null");
+    if (index < 0 || index >= count()) throw Error(ISB_ERR_OUT_OF_RANGE, "compensator index out of range");
+    ISB_ASSERT(w > 0 && h > 0 && pitch >= (size_t)w * 3);
+    cudaStream_t st = current_stream();
+    const float* g;
+    const LinCoefDev *gx, *gy;
+    upload_gain_tables(gains_[index].data(), gw_[index], gh_[index], w, h, aux_, g, gx, gy, st);
+    const bool dev = mem_kind(image) == MemKind::Device;
+    uint8_t* d = image;
+    size_t dp = pitch;
+    if (!dev) {
+        dp = (size_t)w * 3;
+        d = static_cast<uint8_t*>(img_.ensure(dp * h));
+        copy2d(d, dp, image, pitch, dp, h, st);
+    }
+    launch_gain_apply(d, w, h, (long long)dp, g, gw_[index], gh_[index], gx, gy, st);
+    if (!dev) copy2d(image, pitch, d, dp, dp, h, st);
+    ISB_CUDA(cudaStreamSynchronize(st));
+}
+
+void seam_mask_apply(const uint8_t* seam, int mw, int mh, size_t spitch, uint8_t* mask, int w, int h, size_t pitch)
+{
+    require_device();
+    if (!seam || !mask) throw Error(ISB_ERR_NULL_PTR, "seam/mask are null");
+    ISB_ASSERT(mw > 0 && mh > 0 && w > 0 && h > 0 && spitch >= (size_t)mw && pitch >= (size_t)w);
+    cudaStream_t st = current_stream();
+    std::vector<uint32_t> mx, my;
+    build_linear_exact_table(mw, w, mx);
+    build_linear_exact_table(mh, h, my);
+    DevBuf buf;
+    const size_t raw = ((size_t)mw * mh + 255) & ~size_t(255), mb = ((size_t)w * h + 255) & ~size_t(255);
+    char* base = static_cast<char*>(buf.ensure(2 * raw + mb + (mx.size() + my.size()) * sizeof(uint32_t)));
+    uint8_t* sraw = reinterpret_cast<uint8_t*>(base);
+    uint8_t* sdil = sraw + raw;
+    uint8_t* mdev = sdil + raw;
+    uint32_t* tx = reinterpret_cast<uint32_t*>(mdev + mb);
+    uint32_t* ty = tx + mx.size();
+    copy2d(sraw, mw, seam, spitch, mw, mh, st);
+    ISB_CUDA(cudaMemcpyAsync(tx, mx.data(), mx.size() * 4, cudaMemcpyHostToDevice, st));
+    ISB_CUDA(cudaMemcpyAsync(ty, my.data(), my.size() * 4, cudaMemcpyHostToDevice, st));
+    const bool dev = mem_kind(mask) == MemKind::Device;
+    uint8_t* m = mask;
+    size_t mp = pitch;
+    if (!dev) {
+        m = mdev;
+        mp = w;
+        copy2d(m, mp, mask, pitch, w, h, st);
+    }
+    launch_dilate3x3(sraw, mw, mh, mw, sdil, st);
+    launch_seam_and(sdil, mw, mh, tx, ty, m, w, h, (long long)mp, st);
+    if (!dev) copy2d(mask, pitch, m, mp, w, h, st);
+    ISB_CUDA(cudaStreamSynchronize(st));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Blender (classic prepare / feed / blend surface)
+// ------------------------------------------------------------------------------------------------
+void Blender::prepare(const Rect& roi)
+{
+    ISB_ASSERT(roi.w > 0 && roi.h > 0);
+    ISB_ASSERT(requested_ >= 0);
+    BlendGeometry g;
+    g.prepare(roi, requested_);
+    eng_.reset(g, 0, g.roi.h, 0, g.roi.h);
+    prepared_ = true;
+}
+
+void Blender::feed(const int16_t* img, size_t ipitch, const uint8_t* mask, size_t mpitch, int w, int h, int tlx, int tly)
+{
+    require_device();
+    if (!prepared_) throw Error(ISB_ERR_ASSERT, "Assertion failed: prepare() must be called before feed()");
+    if (!img || !mask) throw Error(ISB_ERR_NULL_PTR, "img/mask are null");
+    ISB_ASSERT(w > 0 && h > 0 && ipitch >= (size_t)w * 6 && mpitch >= (size_t)w);
+    cudaStream_t st = current_stream();
+    const int t = eng_.add_tile(-1, w, h, tlx, tly);
+    if (t < 0) return;
+    eng_.commit_tiles(st);
+    const int16_t* di = img;
+    size_t dip = ipitch;
+    if (mem_kind(img) != MemKind::Device) {
+        dip = (size_t)w * 6;
+        void* p = img_.ensure(dip * h);
+        copy2d(p, dip, img, ipitch, dip, h, st);
+        di = static_cast<const int16_t*>(p);
+    }
+    const uint8_t* dm = mask;
+    size_t dmp = mpitch;
+    if (mem_kind(mask) != MemKind::Device) {
+        dmp = w;
+        void* p = mask_.ensure(dmp * h);
+        copy2d(p, dmp, mask, mpitch, w, h, st);
+        dm = static_cast<const uint8_t*>(p);
+    }
+    launch_pack_tile(eng_.tiles_dev() + t, eng_.tiles()[t], di, (long long)dip, dm, (long long)dmp, st);
+    eng_.build_pyramids(t, t + 1, st);
+    ISB_CUDA(cudaStreamSynchronize(st));  // feed keeps no reference to img/mask after it returns
+}
+
+void Blender::blend(int16_t* dst, size_t dpitch, uint8_t* dmask, size_t mpitch)
+{
+    require_device();
+    if (!prepared_) throw Error(ISB_ERR_ASSERT, "Assertion failed: prepare() must be called before blend()");
+    cudaStream_t st = current_stream();
+    const Rect rf = eng_.geom().roi_final;
+    OutDev o{};
+    const bool d16 = dst && mem_kind(dst) == MemKind::Device, dmk = dmask && mem_kind(dmask) == MemKind::Device;
+    if (dst) {
+        ISB_ASSERT(dpitch >= (size_t)rf.w * 6);
+        o.out16 = d16 ? dst : static_cast<int16_t*>(out16_.ensure((size_t)rf.w * 6 * rf.h));
+        o.pitch16 = d16 ? (long long)dpitch : (long long)rf.w * 6;
+    }
+    if (dmask) {
+        ISB_ASSERT(mpitch >= (size_t)rf.w);
+        o.mask = dmk ? dmask : static_cast<uint8_t*>(outm_.ensure((size_t)rf.w * rf.h));
+        o.mpitch = dmk ? (long long)mpitch : rf.w;
+    }
+    eng_.blend(o, st);
+    if (dst && !d16) copy2d(dst, dpitch, o.out16, (size_t)o.pitch16, (size_t)rf.w * 6, rf.h, st);
+    if (dmask && !dmk) copy2d(dmask, mpitch, o.mask, (size_t)o.mpitch, rf.w, rf.h, st);
+    ISB_CUDA(cudaStreamSynchronize(st));
+    prepared_ = false;  // single use per prepare(), as MultiBandBlender::blend releases its pyramids
+}
+
+// ------------------------------------------------------------------------------------------------
+// Composer (fused loop)
+// ------------------------------------------------------------------------------------------------
+enum { ST_H2D = 0, ST_WARP, ST_PYRDOWN, ST_BLEND, ST_D2H, ST_COUNT };
+const char* Composer::stage_name(int i)
+{
+    static const char* names[ST_COUNT] = {"h2d", "warp", "pyrdown", "blend", "d2h"};
+    return (i >= 0 && i < ST_COUNT) ? names[i] : nullptr;
+}
+
+Composer::~Composer()
+{
+    if (ev_init_)
+        for (auto& e : ev_) cudaEventDestroy(e);
+}
+
+bool Composer::same_plan(const isb_camera* cams, const int* sizes_wh, int n) const
+{
+    if (!planned_ || (int)cams_.size() != n) return false;
+    return std::memcmp(cams_.data(), cams, sizeof(isb_camera) * n) == 0 &&
+           std::memcmp(src_sizes_.data(), sizes_wh, sizeof(int) * 2 * n) == 0;
+}
+
+void Composer::plan(const isb_camera* cams, const int* sizes_wh, int n, int* corners, int* sizes, int* dst_roi)
+{
+    if (!cams || !sizes_wh) throw Error(ISB_ERR_NULL_PTR, "cams/sizes are null");
+    ISB_ASSERT(n > 0);
+    ISB_ASSERT(cfg_.warp_kind == ISB_WARP_SPHERICAL || cfg_.warp_kind == ISB_WARP_CYLINDRICAL);
+    ISB_ASSERT(cfg_.strip_count >= 1 && cfg_.strip_index >= 0 && cfg_.strip_index < cfg_.strip_count);
+    ISB_ASSERT(cfg_.num_bands >= 0);
+    if (!(cfg_.cache_plan && same_plan(cams, sizes_wh, n))) {
+        require_device();
+        cudaStream_t st = current_stream();
+        planned_ = false;
+        cams_.assign(cams, cams + n);
+        src_sizes_.assign(sizes_wh, sizes_wh + 2 * n);
+        img_.assign(n, {});
+        // per-image projector + ROI (border forward maps: O(perimeter) atan2f/acosf) - spread over host threads
+        auto work = [&](int i) {
+            ImagePlan& P = img_[i];
+            float K[9];
+            isb_camera_K(&cams[i], K);
+            P.src_w = sizes_wh[2 * i];
+            P.src_h = sizes_wh[2 * i + 1];
+            P.proj.set(cfg_.warp_kind, cfg_.warped_image_scale, K, cams[i].R);
+            P.roi = P.proj.warp_roi(P.src_w, P.src_h);
+        };
+        for (int i = 0; i < n; ++i) ISB_ASSERT(sizes_wh[2 * i] > 0 && sizes_wh[2 * i + 1] > 0);
+        const int nthr = std::max(1, std::min<int>(n, std::min(16u, std::thread::hardware_concurrency())));
+        if (nthr <= 1) {
+            for (int i = 0; i < n; ++i) work(i);
+        } else {
+            std::vector<std::thread> pool;
+            for (int t = 0; t < nthr; ++t)
+                pool.emplace_back([&, t] { for (int i = t; i < n; i += nthr) work(i); });
+            for (auto& th : pool) th.join();
+        }
+        std::vector<int> cs(2 * n), ss(2 * n);
+        for (int i = 0; i < n; ++i) {
+            cs[2 * i] = img_[i].roi.x; cs[2 * i + 1] = img_[i].roi.y;
+            ss[2 * i] = img_[i].roi.w; ss[2 * i + 1] = img_[i].roi.h;
+        }
+        dst_roi_ = result_roi(cs.data(), ss.data(), n);
+        BlendGeometry g;
+        g.prepare(dst_roi_, cfg_.num_bands);
+        // strip: owned rows on the 2^nb grid + halo of 4 * 2^nb rows computed redundantly
+        int y0, y1;
+        strip_rows(g.roi.h, g.nb, cfg_.strip_index, cfg_.strip_count, y0, y1);
+        const int halo = cfg_.strip_count > 1 ? 4 * (1 << g.nb) : 0;
+        const int sy0 = std::max(0, y0 - halo), sy1 = std::min(g.roi.h, y1 + halo);
+        eng_.reset(g, sy0, std::max(sy1 - sy0, 0), y0, y1);
+        tile_of_image_.assign(n, -1);
+        for (int i = 0; i < n; ++i)
+            tile_of_image_[i] = eng_.add_tile(i, img_[i].roi.w, img_[i].roi.h, img_[i].roi.x, img_[i].roi.y);
+        eng_.commit_tiles(st);
+        // separable trig tables + slots for the per-run coefficient tables
+        tables_.begin();
+        for (int i = 0; i < n; ++i) {
+            ImagePlan& P = img_[i];
+            if (tile_of_image_[i] < 0) continue;
+            P.col_off = tables_.take(P.roi.w * sizeof(F2));
+            P.row_off = tables_.take(P.roi.h * sizeof(F2));
+            P.gx_off = tables_.take(P.roi.w * sizeof(LinCoefDev));
+            P.gy_off = tables_.take(P.roi.h * sizeof(LinCoefDev));
+            P.mx_off = tables_.take(P.roi.w * sizeof(uint32_t));
+            P.my_off = tables_.take(P.roi.h * sizeof(uint32_t));
+        }
+        char* tb = tables_.commit();
+        auto tabs = [&](int i) {
+            if (tile_of_image_[i] >= 0) build_trig_tables(img_[i].proj, img_[i].roi, img_[i].col, img_[i].row);
+        };
+        if (nthr <= 1) {
+            for (int i = 0; i < n; ++i) tabs(i);
+        } else {
+            std::vector<std::thread> pool;
+            for (int t = 0; t < nthr; ++t)
+                pool.emplace_back([&, t] { for (int i = t; i < n; i += nthr) tabs(i); });
+            for (auto& th : pool) th.join();
+        }
+        for (int i = 0; i < n; ++i) {
+            ImagePlan& P = img_[i];
+            if (tile_of_image_[i] < 0) continue;
+            ISB_CUDA(cudaMemcpyAsync(tb + P.col_off, P.col.data(), P.col.size() * sizeof(F2), cudaMemcpyHostToDevice, st));
+            ISB_CUDA(cudaMemcpyAsync(tb + P.row_off, P.row.data(), P.row.size() * sizeof(F2), cudaMemcpyHostToDevice, st));
+        }
+        valid_counts_.clear();
+        planned_ = true;
+    }
+    for (int i = 0; i < n; ++i) {
+        if (corners) { corners[2 * i] = img_[i].roi.x; corners[2 * i + 1] = img_[i].roi.y; }
+        if (sizes) { sizes[2 * i] = img_[i].roi.w; sizes[2 * i + 1] = img_[i].roi.h; }
+    }
+    if (dst_roi) { dst_roi[0] = dst_roi_.x; dst_roi[1] = dst_roi_.y; dst_roi[2] = dst_roi_.w; dst_roi[3] = dst_roi_.h; }
+}
+
+void Composer::run(const isb_image* imgs, const isb_gainmap* gains, const isb_mask* seams, int n, isb_pano* out)
+{
+    require_device();
+    if (!planned_) throw Error(ISB_ERR_ASSERT, "Assertion failed: isb_composer_plan() must precede isb_composer_run()");
+    if (!imgs || !out) throw Error(ISB_ERR_NULL_PTR, "imgs/out are null");
+    ISB_ASSERT(n == (int)img_.size());
+    cudaStream_t st = current_stream();
+    if (!ev_init_) {
+        for (auto& e : ev_) ISB_CUDA(cudaEventCreate(&e));
+        ev_init_ = true;
+    }
+    const Rect rf = eng_.geom().roi_final;
+    const int oy0 = std::min(eng_.own_y0(), rf.h), oy1 = std::min(eng_.own_y1(), rf.h);
+
+    // ---- stage 0: inputs to the device -------------------------------------------------------
+    ISB_CUDA(cudaEventRecord(ev_[0], st));
+    dyn_.begin();
+    std::vector<size_t> src_off(n, 0), gain_off(n, 0), sraw_off(n, 0), sdil_off(n, 0);
+    for (int i = 0; i < n; ++i) {
+        if (tile_of_image_[i] < 0) continue;
+        const isb_image& im = imgs[i];
+        if (!im.data) throw Error(ISB_ERR_NULL_PTR, "image data is null");
+        ISB_ASSERT(im.width == img_[i].src_w && im.height == img_[i].src_h && im.pitch >= (size_t)im.width * 3);
+        if (mem_kind(im.data) != MemKind::Device) src_off[i] = dyn_.take((size_t)im.width * 3 * im.height);
+        if (gains && gains[i].data) {
+            ISB_ASSERT(gains[i].width > 0 && gains[i].height > 0);
+            gain_off[i] = dyn_.take((size_t)gains[i].width * gains[i].height * sizeof(float));
+        }
+        if (seams && seams[i].data) {
+            ISB_ASSERT(seams[i].width > 0 && seams[i].height > 0 && seams[i].pitch >= (size_t)seams[i].width);
+            sraw_off[i] = dyn_.take((size_t)seams[i].width * seams[i].height);
+            sdil_off[i] = dyn_.take((size_t)seams[i].width * seams[i].height);
+        }
+    }
+    char* db = dyn_.commit();
+    char* tb = tables_.base();
+    std::vector<ImageDev> idev(n);
+    std::vector<LinCoef> gx, gy;
+    std::vector<uint32_t> mx, my;
+    for (int i = 0; i < n; ++i) {
+        ImageDev& I = idev[i];
+        I = ImageDev{};
+        if (tile_of_image_[i] < 0) continue;
+        const ImagePlan& P = img_[i];
+        const isb_image& im = imgs[i];
+        I.sw = P.src_w; I.sh = P.src_h; I.roi_w = P.roi.w; I.roi_h = P.roi.h;
+        std::memcpy(I.kr, P.proj.k_rinv, sizeof(I.kr));
+        I.col = reinterpret_cast<const F2*>(tb + P.col_off);
+        I.row = reinterpret_cast<const F2*>(tb + P.row_off);
+        if (mem_kind(im.data) == MemKind::Device) {
+            I.src = im.data;
+            I.spitch = (long long)im.pitch;
+        } else {
+            const size_t rb = (size_t)im.width * 3;
+            copy2d(db + src_off[i], rb, im.data, im.pitch, rb, im.height, st);
+            I.src = reinterpret_cast<const uint8_t*>(db + src_off[i]);
+            I.spitch = (long long)rb;
+        }
+        if (gains && gains[i].data) {
+            const isb_gainmap& g = gains[i];
+            ISB_CUDA(cudaMemcpyAsync(db + gain_off[i], g.data, (size_t)g.width * g.height * sizeof(float), cudaMemcpyDefault, st));
+            build_linear_f32_table(g.width, P.roi.w, true, gx);
+            build_linear_f32_table(g.height, P.roi.h, false, gy);
+            ISB_CUDA(cudaMemcpyAsync(tb + P.gx_off, gx.data(), gx.size() * sizeof(LinCoefDev), cudaMemcpyHostToDevice, st));
+            ISB_CUDA(cudaMemcpyAsync(tb + P.gy_off, gy.data(), gy.size() * sizeof(LinCoefDev), cudaMemcpyHostToDevice, st));
+            I.gain = reinterpret_cast<const float*>(db + gain_off[i]);
+            I.gw = g.width; I.gh = g.height;
+            I.gx = reinterpret_cast<const LinCoefDev*>(tb + P.gx_off);
+            I.gy = reinterpret_cast<const LinCoefDev*>(tb + P.gy_off);
+        }
+        if (seams && seams[i].data) {
+            const isb_mask& m = seams[i];
+            copy2d(db + sraw_off[i], m.width, m.data, m.pitch, m.width, m.height, st);
+            build_linear_exact_table(m.width, P.roi.w, mx);
+            build_linear_exact_table(m.height, P.roi.h, my);
+            ISB_CUDA(cudaMemcpyAsync(tb + P.mx_off, mx.data(), mx.size() * 4, cudaMemcpyHostToDevice, st));
+            ISB_CUDA(cudaMemcpyAsync(tb + P.my_off, my.data(), my.size() * 4, cudaMemcpyHostToDevice, st));
+            I.seam = reinterpret_cast<const uint8_t*>(db + sdil_off[i]);
+            I.mw = m.width; I.mh = m.height;
+            I.mx = reinterpret_cast<const uint32_t*>(tb + P.mx_off);
+            I.my = reinterpret_cast<const uint32_t*>(tb + P.my_off);
+        }
+    }
+    ImageDev* idp = static_cast<ImageDev*>(imgs_dev_.ensure(n * sizeof(ImageDev)));
+    ISB_CUDA(cudaMemcpyAsync(idp, idev.data(), n * sizeof(ImageDev), cudaMemcpyHostToDevice, st));
+
+    // ---- stage 1: seam dilate + fused warp (kernel 1) ---------------------------------------
+    ISB_CUDA(cudaEventRecord(ev_[1], st));
+    for (int i = 0; i < n; ++i)
+        if (idev[i].seam)
+            launch_dilate3x3(reinterpret_cast<const uint8_t*>(db + sraw_off[i]), idev[i].mw, idev[i].mh, idev[i].mw,
+                             reinterpret_cast<uint8_t*>(db + sdil_off[i]), st);
+    launch_warp_tiles(eng_.warp_work_dev(), (int)eng_.warp_work().size(), eng_.tiles_dev(), idp, st);
+    // ---- stage 2: pyramids (kernel 2) ---------------------------------------------------------
+    ISB_CUDA(cudaEventRecord(ev_[2], st));
+    eng_.build_pyramids(0, (int)eng_.tiles().size(), st);
+    // ---- stage 3: accumulate + normalise + collapse (kernel 3) --------------------------------
+    ISB_CUDA(cudaEventRecord(ev_[3], st));
+    OutDev o{};
+    const bool d8 = out->data && mem_kind(out->data) == MemKind::Device;
+    const bool dm = out->mask && mem_kind(out->mask) == MemKind::Device;
+    const bool d16 = out->data16 && mem_kind(out->data16) == MemKind::Device;
+    const int sub0 = eng_.sub_y0();
+    // device-side output addressed in sub-panorama rows: row y of the kernel == panorama row y + sub0
+    if (out->data) {
+        ISB_ASSERT(out->pitch >= (size_t)rf.w * 3);
+        if (d8) { o.out8 = out->data + (long long)sub0 * out->pitch; o.pitch8 = (long long)out->pitch; }
+        else {
+            o.pitch8 = (long long)rf.w * 3;
+            o.out8 = static_cast<uint8_t*>(out8_.ensure((size_t)o.pitch8 * std::max(oy1 - oy0, 1))) - (long long)(oy0 - sub0) * o.pitch8;
+        }
+    }
+    if (out->mask) {
+        ISB_ASSERT(out->mask_pitch >= (size_t)rf.w);
+        if (dm) { o.mask = out->mask + (long long)sub0 * out->mask_pitch; o.mpitch = (long long)out->mask_pitch; }
+        else {
+            o.mpitch = rf.w;
+            o.mask = static_cast<uint8_t*>(outm_.ensure((size_t)o.mpitch * std::max(oy1 - oy0, 1))) - (long long)(oy0 - sub0) * o.mpitch;
+        }
+    }
+    if (out->data16) {
+        ISB_ASSERT(out->pitch16 >= (size_t)rf.w * 6);
+        if (d16) { o.out16 = reinterpret_cast<int16_t*>(reinterpret_cast<char*>(out->data16) + (long long)sub0 * out->pitch16); o.pitch16 = (long long)out->pitch16; }
+        else {
+            o.pitch16 = (long long)rf.w * 6;
+            o.out16 = reinterpret_cast<int16_t*>(static_cast<char*>(out16_.ensure((size_t)o.pitch16 * std::max(oy1 - oy0, 1))) - (long long)(oy0 - sub0) * o.pitch16);
+        }
+    }
+    eng_.blend(o, st);
+    // ---- stage 4: results to the host ---------------------------------------------------------
+    ISB_CUDA(cudaEventRecord(ev_[4], st));
+    const int rows = std::max(oy1 - oy0, 0);
+    if (out->data && !d8) copy2d(out->data + (size_t)oy0 * out->pitch, out->pitch, out8_.as<uint8_t>(), (size_t)o.pitch8, (size_t)rf.w * 3, rows, st);
+    if (out->mask && !dm) copy2d(out->mask + (size_t)oy0 * out->mask_pitch, out->mask_pitch, outm_.as<uint8_t>(), (size_t)o.mpitch, rf.w, rows, st);
+    if (out->data16 && !d16)
+        copy2d(reinterpret_cast<char*>(out->data16) + (size_t)oy0 * out->pitch16, out->pitch16, out16_.as<char>(), (size_t)o.pitch16, (size_t)rf.w * 6, rows, st);
+    ISB_CUDA(cudaEventRecord(ev_[5], st));
+    out->roi_xywh[0] = rf.x; out->roi_xywh[1] = rf.y; out->roi_xywh[2] = rf.w; out->roi_xywh[3] = rf.h;
+    out->strip_y0 = oy0;
+    out->strip_y1 = oy1;
+    // host-visible results (or host-owned inputs) => the call is synchronous; all-device calls stay stream-ordered
+    bool any_host = (out->data && !d8) || (out->mask && !dm) || (out->data16 && !d16);
+    for (int i = 0; i < n && !any_host; ++i)
+        if (tile_of_image_[i] >= 0 && mem_kind(imgs[i].data) == MemKind::Host) any_host = true;
+    if (any_host) ISB_CUDA(cudaStreamSynchronize(st));
+}
+
+int Composer::timings(float* ms, int cap)
+{
+    if (!ev_init_) return 0;
+    ISB_CUDA(cudaEventSynchronize(ev_[5]));
+    for (int i = 0; i < ST_COUNT; ++i) {
+        float v = 0.f;
+        ISB_CUDA(cudaEventElapsedTime(&v, ev_[i], ev_[i + 1]));
+        last_ms_[i] = v;
+        if (ms && i < cap) ms[i] = v;
+    }
+    return ST_COUNT;
+}
+
+void Composer::byte_model(double* S, double* M, double* Ap, double* B)
+{
+    if (!planned_) throw Error(ISB_ERR_ASSERT, "Assertion failed: plan() first");
+    require_device();
+    const int n = (int)img_.size();
+    cudaStream_t st = current_stream();
+    if (valid_counts_.empty()) {
+        // M = number of non-zero pixels of the nearest-warped masks, counted by the device inverse map
+        std::vector<ImageDev> idev(n);
+        std::vector<int> rw(n), rh(n);
+        DevBuf tabs;
+        Arena a;
+        a.begin();
+        std::vector<size_t> co(n), ro(n);
+        std::vector<std::vector<Float2>> cols(n), rows(n);
+        for (int i = 0; i < n; ++i) {
+            build_trig_tables(img_[i].proj, img_[i].roi, cols[i], rows[i]);
+            co[i] = a.take(cols[i].size() * sizeof(F2));
+            ro[i] = a.take(rows[i].size() * sizeof(F2));
+        }
+        char* base = a.commit();
+        for (int i = 0; i < n; ++i) {
+            ISB_CUDA(cudaMemcpyAsync(base + co[i], cols[i].data(), cols[i].size() * sizeof(F2), cudaMemcpyHostToDevice, st));
+            ISB_CUDA(cudaMemcpyAsync(base + ro[i], rows[i].data(), rows[i].size() * sizeof(F2), cudaMemcpyHostToDevice, st));
+            ImageDev& I = idev[i];
+            I = ImageDev{};
+            I.sw = img_[i].src_w; I.sh = img_[i].src_h; I.roi_w = rw[i] = img_[i].roi.w; I.roi_h = rh[i] = img_[i].roi.h;
+            std::memcpy(I.kr, img_[i].proj.k_rinv, sizeof(I.kr));
+            I.col = reinterpret_cast<const F2*>(base + co[i]);
+            I.row = reinterpret_cast<const F2*>(base + ro[i]);
+        }
+        DevBuf idb;
+        ImageDev* idp = static_cast<ImageDev*>(idb.ensure(n * sizeof(ImageDev)));
+        ISB_CUDA(cudaMemcpyAsync(idp, idev.data(), n * sizeof(ImageDev), cudaMemcpyHostToDevice, st));
+        unsigned long long* cd = static_cast<unsigned long long*>(counts_dev_.ensure(n * sizeof(unsigned long long)));
+        ISB_CUDA(cudaMemsetAsync(cd, 0, n * sizeof(unsigned long long), st));
+        launch_count_valid(idp, n, rw.data(), rh.data(), cd, st);
+        valid_counts_.resize(n);
+        ISB_CUDA(cudaMemcpyAsync(valid_counts_.data(), cd, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        ISB_CUDA(cudaStreamSynchronize(st));
+    }
+    double s = 0, m = 0;
+    for (int i = 0; i < n; ++i) {
+        s += (double)img_[i].src_w * img_[i].src_h;
+        m += (double)valid_counts_[i];
+    }
+    const double ap = (double)dst_roi_.w * dst_roi_.h;
+    double P = 0;
+    for (int l = 0; l <= eng_.geom().nb; ++l) P += std::pow(4.0, -l);
+    if (S) *S = s;
+    if (M) *M = m;
+    if (Ap) *Ap = ap;
+    if (B) *B = 3 * s + 40 * P * m + 10 * P * ap + 4 * ap;
+}
+
+}  // namespace isb

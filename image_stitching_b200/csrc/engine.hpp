@@ -1,0 +1,216 @@
+// engine.hpp - host-side objects behind the C ABI: device buffers, the pyramid engine shared by the
+// classic MultiBandBlender surface and the fused composer, and the warper / compensator mirrors.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/image_stitching.h"
+#include "device_types.hpp"
+#include "geometry.hpp"
+
+namespace isb {
+
+// Errors travel as exceptions inside the library and are converted to codes at the C boundary.
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+#define ISB_ASSERT(cond)                                                                                  \
+    do {                                                                                                  \
+        if (!(cond)) throw ::isb::Error(ISB_ERR_ASSERT, std::string("Assertion failed: ") + #cond);      \
+    } while (0)
+void cuda_check(cudaError_t e, const char* what);
+#define ISB_CUDA(call) ::isb::cuda_check((call), #call)
+
+cudaStream_t current_stream();
+void set_current_stream(cudaStream_t s);
+void require_device();  // throws ISB_ERR_GPU_API when no CUDA device is usable (no CPU fallback exists)
+
+enum class MemKind { Host, HostPinned, Device };
+MemKind mem_kind(const void* p);
+
+// growable device allocation (never shrinks; reused across calls)
+class DevBuf {
+public:
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf();
+    void* ensure(size_t bytes);
+    template <typename T> T* as() const { return static_cast<T*>(p_); }
+    size_t capacity() const { return cap_; }
+private:
+    void* p_ = nullptr;
+    size_t cap_ = 0;
+};
+
+// growable pinned host allocation used to stage small descriptor uploads
+class PinBuf {
+public:
+    PinBuf() = default;
+    PinBuf(const PinBuf&) = delete;
+    PinBuf& operator=(const PinBuf&) = delete;
+    ~PinBuf();
+    void* ensure(size_t bytes);
+private:
+    void* p_ = nullptr;
+    size_t cap_ = 0;
+};
+
+// bump allocator over one device block; sized by a dry run, then replayed
+class Arena {
+public:
+    void begin() { off_ = 0; }
+    size_t take(size_t bytes) { size_t o = off_; off_ = (off_ + bytes + 255) & ~size_t(255); return o; }
+    size_t used() const { return off_; }
+    char* commit() { return static_cast<char*>(buf_.ensure(off_ ? off_ : 256)); }
+    char* base() const { return buf_.as<char>(); }
+private:
+    DevBuf buf_;
+    size_t off_ = 0;
+};
+
+// per-image inputs of the fused warp that do not depend on pixel data (built at plan time)
+struct ImagePlan {
+    Projector proj;
+    Rect roi;            // warpRoi
+    int src_w = 0, src_h = 0;
+    std::vector<Float2> col, row;
+    // offsets into the composer's table arena
+    size_t col_off = 0, row_off = 0, gx_off = 0, gy_off = 0, mx_off = 0, my_off = 0;
+};
+
+// The pyramid engine: owns the per-tile pyramids and the destination pyramid, runs kernels 2 and 3.
+class PyramidEngine {
+public:
+    // Start a blend over the sub-panorama rows [sub_y0, sub_y0 + sub_h) of the padded ROI; rows
+    // [own_y0, own_y1) (padded coords) are the ones written to the output.
+    void reset(const BlendGeometry& g, int sub_y0, int sub_h, int own_y0, int own_y1);
+    // Add the tile feed() would use for an image at `tl` of size (w x h); clipped to the sub-panorama.
+    // Returns the tile index or -1 when the tile does not touch the sub-panorama.
+    int add_tile(int img_index, int w, int h, int tlx, int tly);
+    // Allocate pyramid storage for tiles [first, end) (device pointers filled in), upload descriptors.
+    void commit_tiles(cudaStream_t st);
+    // kernel 2 for tiles [first, end): all levels
+    void build_pyramids(int first, int end, cudaStream_t st);
+    // kernel 3 for all levels; writes the owned rows
+    void blend(const OutDev& out, cudaStream_t st);
+
+    const BlendGeometry& geom() const { return g_; }
+    std::vector<TileDev>& tiles() { return tiles_; }
+    const TileDev* tiles_dev() const { return tiles_dev_.as<TileDev>(); }
+    int sub_y0() const { return sub_y0_; }
+    int own_y0() const { return own_y0_; }
+    int own_y1() const { return own_y1_; }
+    const std::vector<WorkItem>& warp_work() const { return warp_work_; }
+    const WorkItem* warp_work_dev() const { return warp_work_dev_.as<WorkItem>(); }
+    size_t pyramid_bytes() const { return arena_.used(); }
+
+private:
+    BlendGeometry g_;
+    int sub_y0_ = 0, sub_h_ = 0, own_y0_ = 0, own_y1_ = 0;
+    std::vector<TileDev> tiles_;
+    int committed_ = 0;           // tiles [0, committed_) have storage
+    std::vector<size_t> tile_off_;  // arena offset of each tile's storage
+    Arena arena_;                 // fused path: one block for all tiles
+    std::vector<DevBuf*> extra_;  // classic path: one allocation per late-added tile
+    DevBuf tiles_dev_, warp_work_dev_, down_work_dev_, cells_dev_, dst_buf_;
+    std::vector<WorkItem> warp_work_;
+    std::vector<std::vector<WorkItem>> down_work_;  // per level, for tiles of the last commit
+    std::vector<size_t> down_off_;
+    PinBuf pin_;
+    DstDev dst_{};
+    bool frozen_arena_ = false;
+public:
+    ~PyramidEngine();
+};
+
+class Warper {
+public:
+    Warper(int kind, float scale) : kind_(kind), scale_(scale) {}
+    int kind() const { return kind_; }
+    float scale() const { return scale_; }
+    void set_scale(float s) { scale_ = s; }
+    Rect warp_roi(int sw, int sh, const float* K, const float* R);
+    void warp_point(const float* pt, const float* K, const float* R, float* out, bool backward);
+    Rect build_maps(int sw, int sh, const float* K, const float* R, float* xmap, float* ymap, size_t pitch);
+    void warp(const uint8_t* src, int sw, int sh, int ch, size_t spitch, const float* K, const float* R, int interp,
+              int border, uint8_t* dst, size_t dpitch, int* corner);
+private:
+    void prepare_image(int sw, int sh, const float* K, const float* R, ImageDev& I, Rect& roi, cudaStream_t st);
+    int kind_;
+    float scale_;
+    DevBuf src_, dst_, tab_, xm_, ym_;
+    PinBuf pin_;
+};
+
+class Compensator {
+public:
+    Compensator(int bw, int bh) : bw_(bw), bh_(bh) {}
+    void set_gains(int n, const float* const* g, const int* gw, const int* gh);
+    int count() const { return (int)gains_.size(); }
+    const std::vector<float>& gain(int i, int& w, int& h) const { w = gw_[i]; h = gh_[i]; return gains_[i]; }
+    void apply(int index, uint8_t* image, int w, int h, size_t pitch);
+private:
+    int bw_, bh_;
+    std::vector<std::vector<float>> gains_;
+    std::vector<int> gw_, gh_;
+    DevBuf img_, aux_;
+    PinBuf pin_;
+};
+
+void seam_mask_apply(const uint8_t* seam, int mw, int mh, size_t spitch, uint8_t* mask, int w, int h, size_t pitch);
+
+class Blender {
+public:
+    explicit Blender(int nb) : requested_(nb) {}
+    void set_num_bands(int nb) { requested_ = nb; }
+    int num_bands() const { return requested_; }
+    int actual_bands() const { return eng_.geom().nb; }
+    bool prepared() const { return prepared_; }
+    void prepare(const Rect& roi);
+    const BlendGeometry& geom() const { return eng_.geom(); }
+    void feed(const int16_t* img, size_t ipitch, const uint8_t* mask, size_t mpitch, int w, int h, int tlx, int tly);
+    void blend(int16_t* dst, size_t dpitch, uint8_t* dmask, size_t mpitch);
+private:
+    int requested_;
+    bool prepared_ = false;
+    PyramidEngine eng_;
+    DevBuf img_, mask_, out16_, outm_;
+};
+
+class Composer {
+public:
+    explicit Composer(const isb_config& cfg) : cfg_(cfg) {}
+    void plan(const isb_camera* cams, const int* sizes_wh, int n, int* corners, int* sizes, int* dst_roi);
+    void run(const isb_image* imgs, const isb_gainmap* gains, const isb_mask* seams, int n, isb_pano* out);
+    int timings(float* ms, int cap);
+    void byte_model(double* S, double* M, double* Ap, double* B);
+    static const char* stage_name(int i);
+private:
+    bool same_plan(const isb_camera* cams, const int* sizes_wh, int n) const;
+    isb_config cfg_;
+    bool planned_ = false;
+    std::vector<isb_camera> cams_;
+    std::vector<int> src_sizes_;
+    std::vector<ImagePlan> img_;
+    std::vector<int> tile_of_image_;
+    PyramidEngine eng_;
+    Rect dst_roi_;
+    Arena tables_;              // trig tables (static per plan)
+    Arena dyn_;                 // per-run uploads: sources, gains, seam masks, their coefficient tables
+    DevBuf imgs_dev_, counts_dev_, out8_, outm_, out16_;
+    PinBuf pin_, pin_tab_;
+    std::vector<unsigned long long> valid_counts_;
+    cudaEvent_t ev_[8] = {};
+    bool ev_init_ = false;
+    float last_ms_[8] = {};
+public:
+    ~Composer();
+};
+
+}  // namespace isb

@@ -1,0 +1,572 @@
+// kernels.cu - hand-written sm_100a kernels of the compositing hot path.
+//
+// Arithmetic contract (each item pinned against OpenCV 4.13 by the oracle):
+//  * every float op of the inverse map / gain / weight pyramid rounds to binary32 on its own
+//    (__fmul_rn/__fadd_rn/__fdiv_rn; the file is also built with -fmad=false);
+//  * 8-bit bilinear sampling is the 1/32-px fixed-point remap (A.3); masks use nearest/half-even;
+//  * 16S pyramids are pure integer (A.5); weight pyramids reproduce OpenCV's SIMD/scalar op order;
+//  * accumulate / normalise truncate toward zero and wrap to int16 exactly like the C++ casts (A.6).
+// None of this is a dense contraction, so no tensor cores: the kernels are HBM/LSU bound.
+#include <climits>
+#include <cstdint>
+
+#include "kernels.cuh"
+
+namespace isb {
+
+static long long g_launches = 0;
+long long launch_count(bool reset)
+{
+    long long v = g_launches;
+    if (reset) g_launches = 0;
+    return v;
+}
+#define ISB_COUNT_LAUNCH() (++g_launches)
+
+// ------------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int cv_round(float v)
+{  // cvRound on x86 (cvtss2si): half-to-even, INT_MIN when out of range or NaN
+    return (fabsf(v) < 2147483648.f) ? __float2int_rn(v) : INT_MIN;
+}
+__device__ __forceinline__ int sat_s16(int v) { return min(max(v, -32768), 32767); }
+__device__ __forceinline__ int sat_u8(int v) { return min(max(v, 0), 255); }
+// static_cast<short>(float): cvttss2si then the low 16 bits
+__device__ __forceinline__ int trunc_s16(float v) { return (int)(short)__float2int_rz(v); }
+
+__device__ __forceinline__ int reflect(int p, int n)
+{  // cv::BORDER_REFLECT  fedcba|abcdefgh|hgfedcb, any distance
+    if ((unsigned)p < (unsigned)n) return p;
+    if (n == 1) return 0;
+    if (p < 0) p = -p - 1;
+    const int m = 2 * n;
+    p %= m;
+    return p < n ? p : m - 1 - p;
+}
+__device__ __forceinline__ int reflect101(int p, int n)
+{  // cv::BORDER_REFLECT_101 for |overshoot| < n (pyramid taps overshoot by <= 2)
+    if (n == 1) return 0;
+    if (p < 0) p = -p;
+    if (p >= n) p = 2 * n - 2 - p;
+    return max(p, 0);
+}
+
+struct XY { float x, y; };
+
+// mapBackward with the transcendentals taken from the separable host tables (A.2)
+__device__ __forceinline__ XY inverse_map(const float* __restrict__ kr, F2 c, F2 r)
+{
+    const float x_ = __fmul_rn(r.a, c.a), y_ = r.b, z_ = __fmul_rn(r.a, c.b);
+    float x = __fadd_rn(__fadd_rn(__fmul_rn(kr[0], x_), __fmul_rn(kr[1], y_)), __fmul_rn(kr[2], z_));
+    float y = __fadd_rn(__fadd_rn(__fmul_rn(kr[3], x_), __fmul_rn(kr[4], y_)), __fmul_rn(kr[5], z_));
+    const float z = __fadd_rn(__fadd_rn(__fmul_rn(kr[6], x_), __fmul_rn(kr[7], y_)), __fmul_rn(kr[8], z_));
+    if (z > 0.f) {
+        x = __fdiv_rn(x, z);
+        y = __fdiv_rn(y, z);
+    } else {
+        x = y = -1.f;
+    }
+    return XY{x, y};
+}
+
+// cv::remap INTER_LINEAR on 8U: fixed-point coordinates (1/32 px) and 15-bit weights (A.3)
+struct BilinearTaps {
+    int x0, y0, w00, w01, w10, w11;
+};
+__device__ __forceinline__ BilinearTaps bilinear_taps(XY m)
+{
+    const int sx = cv_round(__fmul_rn(m.x, 32.f)), sy = cv_round(__fmul_rn(m.y, 32.f));
+    BilinearTaps t;
+    t.x0 = sat_s16(sx >> 5);
+    t.y0 = sat_s16(sy >> 5);
+    const int a = sx & 31, b = sy & 31;
+    t.w00 = (32 - a) * (32 - b) * 32;
+    t.w01 = a * (32 - b) * 32;
+    t.w10 = (32 - a) * b * 32;
+    t.w11 = a * b * 32;
+    return t;
+}
+
+template <int CH, bool REFLECT>
+__device__ __forceinline__ void sample_linear(const ImageDev& I, XY m, int out[CH])
+{
+    const BilinearTaps t = bilinear_taps(m);
+    int xa = t.x0, xb = t.x0 + 1, ya = t.y0, yb = t.y0 + 1;
+    bool vxa = true, vxb = true, vya = true, vyb = true;
+    if (REFLECT) {
+        xa = reflect(xa, I.sw); xb = reflect(xb, I.sw); ya = reflect(ya, I.sh); yb = reflect(yb, I.sh);
+    } else {
+        vxa = (unsigned)xa < (unsigned)I.sw; vxb = (unsigned)xb < (unsigned)I.sw;
+        vya = (unsigned)ya < (unsigned)I.sh; vyb = (unsigned)yb < (unsigned)I.sh;
+        xa = vxa ? xa : 0; xb = vxb ? xb : 0; ya = vya ? ya : 0; yb = vyb ? yb : 0;
+    }
+    const uint8_t* ra = I.src + (long long)ya * I.spitch;
+    const uint8_t* rb = I.src + (long long)yb * I.spitch;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+        const int p00 = (vxa && vya) ? __ldg(ra + xa * CH + c) : 0;
+        const int p01 = (vxb && vya) ? __ldg(ra + xb * CH + c) : 0;
+        const int p10 = (vxa && vyb) ? __ldg(rb + xa * CH + c) : 0;
+        const int p11 = (vxb && vyb) ? __ldg(rb + xb * CH + c) : 0;
+        out[c] = sat_u8((p00 * t.w00 + p01 * t.w01 + p10 * t.w10 + p11 * t.w11 + (1 << 14)) >> 15);
+    }
+}
+
+// validity of the nearest/constant mask warp: 255 iff round-half-even(x), (y) fall inside the source
+__device__ __forceinline__ bool nearest_inside(const ImageDev& I, XY m, int& ix, int& iy)
+{
+    ix = sat_s16(cv_round(m.x));
+    iy = sat_s16(cv_round(m.y));
+    return (unsigned)ix < (unsigned)I.sw && (unsigned)iy < (unsigned)I.sh;
+}
+
+// cv::resize(f32, INTER_LINEAR) of the gain grid evaluated at one ROI pixel (A.7)
+__device__ __forceinline__ float gain_at(const ImageDev& I, LinCoefDev cx, LinCoefDev cy)
+{
+    const int c0 = cx.ofs, c1 = min(cx.ofs + 1, I.gw - 1);
+    const int r0 = min(max(cy.ofs, 0), I.gh - 1), r1 = min(max(cy.ofs + 1, 0), I.gh - 1);
+    const float a1 = cx.frac, a0 = __fsub_rn(1.f, a1), b1 = cy.frac, b0 = __fsub_rn(1.f, b1);
+    const float* g0 = I.gain + r0 * I.gw;
+    const float* g1 = I.gain + r1 * I.gw;
+    const float h0 = __fadd_rn(__fmul_rn(__ldg(g0 + c0), a0), __fmul_rn(__ldg(g0 + c1), a1));
+    const float h1 = __fadd_rn(__fmul_rn(__ldg(g1 + c0), a0), __fmul_rn(__ldg(g1 + c1), a1));
+    return __fadd_rn(__fmul_rn(h0, b0), __fmul_rn(h1, b1));
+}
+
+// cv::resize(8U, INTER_LINEAR_EXACT) of the dilated seam mask at one ROI pixel (A.4)
+__device__ __forceinline__ int seam_at(const uint8_t* __restrict__ dil, int mw, int mh, uint32_t tx, uint32_t ty)
+{
+    const int c0 = tx >> 16, ax = tx & 0xffff, r0 = ty >> 16, ay = ty & 0xffff;
+    const int c1 = min(c0 + 1, mw - 1), r1 = min(r0 + 1, mh - 1);
+    const uint8_t* p0 = dil + r0 * mw;
+    const uint8_t* p1 = dil + r1 * mw;
+    const int h0 = __ldg(p0 + c0) * (256 - ax) + __ldg(p0 + c1) * ax;
+    const int h1 = __ldg(p1 + c0) * (256 - ax) + __ldg(p1 + c1) * ax;
+    return (h0 * (256 - ay) + h1 * ay + 32768) >> 16;
+}
+
+// ------------------------------------------------------------------------------------------------
+// classic API kernels
+// ------------------------------------------------------------------------------------------------
+template <int CH>
+__global__ void __launch_bounds__(256) warp_generic_kernel(ImageDev I, int interp, int border, uint8_t* __restrict__ dst,
+                                                           long long dpitch)
+{
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= I.roi_w || y >= I.roi_h) return;
+    const XY m = inverse_map(I.kr, I.col[x], I.row[y]);
+    int v[CH];
+    if (interp == 1) {
+        if (border == 2) sample_linear<CH, true>(I, m, v);
+        else sample_linear<CH, false>(I, m, v);
+    } else {
+        int ix, iy;
+        const bool in = nearest_inside(I, m, ix, iy);
+        if (border == 2) {
+            ix = reflect(ix, I.sw);
+            iy = reflect(iy, I.sh);
+        }
+#pragma unroll
+        for (int c = 0; c < CH; ++c) v[c] = (in || border == 2) ? I.src[(long long)iy * I.spitch + ix * CH + c] : 0;
+    }
+#pragma unroll
+    for (int c = 0; c < CH; ++c) dst[(long long)y * dpitch + x * CH + c] = (uint8_t)v[c];
+}
+
+void launch_warp_generic(const ImageDev& img, int ch, int interp, int border, uint8_t* dst, long long dpitch,
+                         cudaStream_t st)
+{
+    dim3 grid((img.roi_w + 31) / 32, (img.roi_h + 7) / 8);
+    if (ch == 3) warp_generic_kernel<3><<<grid, 256, 0, st>>>(img, interp, border, dst, dpitch);
+    else warp_generic_kernel<1><<<grid, 256, 0, st>>>(img, interp, border, dst, dpitch);
+    ISB_COUNT_LAUNCH();
+}
+
+__global__ void __launch_bounds__(256) build_maps_kernel(ImageDev I, float* __restrict__ xmap, float* __restrict__ ymap,
+                                                         long long pitch_bytes)
+{
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= I.roi_w || y >= I.roi_h) return;
+    const XY m = inverse_map(I.kr, I.col[x], I.row[y]);
+    reinterpret_cast<float*>(reinterpret_cast<char*>(xmap) + y * pitch_bytes)[x] = m.x;
+    reinterpret_cast<float*>(reinterpret_cast<char*>(ymap) + y * pitch_bytes)[x] = m.y;
+}
+
+void launch_build_maps(const ImageDev& img, float* xmap, float* ymap, long long pitch_bytes, cudaStream_t st)
+{
+    dim3 grid((img.roi_w + 31) / 32, (img.roi_h + 7) / 8);
+    build_maps_kernel<<<grid, 256, 0, st>>>(img, xmap, ymap, pitch_bytes);
+    ISB_COUNT_LAUNCH();
+}
+
+__global__ void __launch_bounds__(256) gain_apply_kernel(uint8_t* __restrict__ img, int w, int h, long long pitch,
+                                                         ImageDev I)
+{
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= w || y >= h) return;
+    const float g = gain_at(I, I.gx[x], I.gy[y]);
+    uint8_t* p = img + y * pitch + x * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) p[c] = (uint8_t)sat_u8(cv_round(__fmul_rn((float)p[c], g)));
+}
+
+void launch_gain_apply(uint8_t* img, int w, int h, long long pitch, const float* gain, int gw, int gh,
+                       const LinCoefDev* gx, const LinCoefDev* gy, cudaStream_t st)
+{
+    ImageDev I{};
+    I.gain = gain; I.gw = gw; I.gh = gh; I.gx = gx; I.gy = gy;
+    dim3 grid((w + 31) / 32, (h + 7) / 8);
+    gain_apply_kernel<<<grid, 256, 0, st>>>(img, w, h, pitch, I);
+    ISB_COUNT_LAUNCH();
+}
+
+__global__ void __launch_bounds__(256) dilate3x3_kernel(const uint8_t* __restrict__ src, int w, int h, long long spitch,
+                                                        uint8_t* __restrict__ dst)
+{
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= w || y >= h) return;
+    int m = 0;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) {
+            const int yy = y + dy, xx = x + dx;
+            if ((unsigned)yy < (unsigned)h && (unsigned)xx < (unsigned)w) m = max(m, (int)src[yy * spitch + xx]);
+        }
+    dst[y * w + x] = (uint8_t)m;
+}
+
+void launch_dilate3x3(const uint8_t* src, int w, int h, long long spitch, uint8_t* dst, cudaStream_t st)
+{
+    dim3 grid((w + 31) / 32, (h + 7) / 8);
+    dilate3x3_kernel<<<grid, 256, 0, st>>>(src, w, h, spitch, dst);
+    ISB_COUNT_LAUNCH();
+}
+
+__global__ void __launch_bounds__(256) seam_and_kernel(const uint8_t* __restrict__ dil, int mw, int mh,
+                                                       const uint32_t* __restrict__ mx, const uint32_t* __restrict__ my,
+                                                       uint8_t* __restrict__ mask, int w, int h, long long pitch)
+{
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= w || y >= h) return;
+    mask[y * pitch + x] &= (uint8_t)seam_at(dil, mw, mh, mx[x], my[y]);
+}
+
+void launch_seam_and(const uint8_t* dil, int mw, int mh, const uint32_t* mx, const uint32_t* my, uint8_t* mask, int w,
+                     int h, long long pitch, cudaStream_t st)
+{
+    dim3 grid((w + 31) / 32, (h + 7) / 8);
+    seam_and_kernel<<<grid, 256, 0, st>>>(dil, mw, mh, mx, my, mask, w, h, pitch);
+    ISB_COUNT_LAUNCH();
+}
+
+__global__ void __launch_bounds__(256) pack_tile_kernel(const TileDev* __restrict__ tp, const int16_t* __restrict__ img,
+                                                        long long ipitch, const uint8_t* __restrict__ mask,
+                                                        long long mpitch)
+{
+    const TileDev& T = *tp;
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= T.w || y >= T.h) return;
+    const int rx0 = x - T.left, ry0 = y - T.top;
+    const bool in = (unsigned)rx0 < (unsigned)T.roi_w && (unsigned)ry0 < (unsigned)T.roi_h;
+    const int rx = reflect(rx0, T.roi_w), ry = reflect(ry0, T.roi_h);
+    const int16_t* p = reinterpret_cast<const int16_t*>(reinterpret_cast<const char*>(img) + ry * ipitch) + rx * 3;
+    int16_t* g = T.G[0] + (long long)y * T.gpitch[0] + x;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) g[c * T.gplane[0]] = p[c];
+    const float inv255 = (float)(1. / 255.);
+    T.W[0][(long long)y * T.wpitch[0] + x] = in ? __fmul_rn((float)mask[ry * mpitch + rx], inv255) : 0.f;
+}
+
+void launch_pack_tile(const TileDev* tile_dev, const TileDev& tile_host, const int16_t* img, long long ipitch,
+                      const uint8_t* mask, long long mpitch, cudaStream_t st)
+{
+    dim3 grid((tile_host.w + 31) / 32, (tile_host.h + 7) / 8);
+    pack_tile_kernel<<<grid, 256, 0, st>>>(tile_dev, img, ipitch, mask, mpitch);
+    ISB_COUNT_LAUNCH();
+}
+
+// ------------------------------------------------------------------------------------------------
+// plan-time: count valid warped pixels (M of the byte model)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) count_valid_kernel(const ImageDev* __restrict__ imgs,
+                                                          unsigned long long* __restrict__ counts)
+{
+    const ImageDev& I = imgs[blockIdx.z];
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    int cnt = 0;
+    if (x < I.roi_w) {
+        const F2 c = I.col[x];
+        const int y0 = blockIdx.y * 64 + (threadIdx.x >> 5);
+        for (int k = 0; k < 8; ++k) {
+            const int y = y0 + 8 * k;
+            if (y >= I.roi_h) break;
+            int ix, iy;
+            cnt += nearest_inside(I, inverse_map(I.kr, c, I.row[y]), ix, iy) ? 1 : 0;
+        }
+    }
+    // warp-shuffle reduction, one atomic per warp
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(counts + blockIdx.z, (unsigned long long)cnt);
+}
+
+void launch_count_valid(const ImageDev* imgs_dev, int n_img, const int* roi_w_host, const int* roi_h_host,
+                        unsigned long long* counts_dev, cudaStream_t st)
+{
+    int mw = 0, mh = 0;
+    for (int i = 0; i < n_img; ++i) {
+        mw = max(mw, roi_w_host[i]);
+        mh = max(mh, roi_h_host[i]);
+    }
+    if (mw == 0 || mh == 0) return;
+    for (int z0 = 0; z0 < n_img; z0 += 65535) {
+        dim3 grid((mw + 31) / 32, (mh + 63) / 64, min(65535, n_img - z0));
+        count_valid_kernel<<<grid, 256, 0, st>>>(imgs_dev + z0, counts_dev + z0);
+        ISB_COUNT_LAUNCH();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel 1: fused warp -> level 0 of the per-image pyramids
+//   G0 = REFLECT-padded  sat_u8(rint(bilinear(src at R*K^-1 map) * gain))  as 16S, planar
+//   W0 = (seam_up & valid) / 255 inside the ROI, 0 in the padding
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) warp_tiles_kernel(const WorkItem* __restrict__ work, const TileDev* __restrict__ tiles,
+                                                         const ImageDev* __restrict__ imgs)
+{
+    const WorkItem wi = work[blockIdx.x];
+    const TileDev& T = tiles[wi.tile];
+    const ImageDev& I = imgs[T.img];
+    const int x = wi.bx * kWarpBlockW + (threadIdx.x & 63);
+    if (x >= T.w) return;
+    const int rx0 = x - T.left;
+    const bool in_x = (unsigned)rx0 < (unsigned)I.roi_w;
+    const int rx = reflect(rx0, I.roi_w);
+    const F2 col = I.col[rx];
+    const bool has_gain = I.gain != nullptr, has_seam = I.seam != nullptr;
+    LinCoefDev gx{0, 0.f};
+    uint32_t mx = 0;
+    if (has_gain) gx = I.gx[rx];
+    if (has_seam) mx = I.mx[rx];
+    const float inv255 = (float)(1. / 255.);
+    const int ybase = wi.by * kWarpBlockH + (threadIdx.x >> 6);
+    int16_t* __restrict__ G = T.G[0];
+    float* __restrict__ W = T.W[0];
+    const int gp = T.gpitch[0], wp = T.wpitch[0];
+    const long long plane = T.gplane[0];
+#pragma unroll 2
+    for (int k = 0; k < kWarpBlockH / 4; ++k) {
+        const int y = ybase + 4 * k;
+        if (y >= T.h) break;
+        const int ry0 = y - T.top;
+        const bool in = in_x && (unsigned)ry0 < (unsigned)I.roi_h;
+        const int ry = reflect(ry0, I.roi_h);
+        const XY m = inverse_map(I.kr, col, I.row[ry]);
+        int v[3];
+        sample_linear<3, true>(I, m, v);
+        if (has_gain) {
+            const float g = gain_at(I, gx, I.gy[ry]);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v[c] = sat_u8(cv_round(__fmul_rn((float)v[c], g)));
+        }
+        float w = 0.f;
+        if (in) {
+            int ix, iy;
+            int mval = nearest_inside(I, m, ix, iy) ? 255 : 0;
+            if (has_seam && mval) mval &= seam_at(I.seam, I.mw, I.mh, mx, I.my[ry]);
+            w = __fmul_rn((float)mval, inv255);
+        }
+        const long long o = (long long)y * gp + x;
+        G[o] = (int16_t)v[0];
+        G[o + plane] = (int16_t)v[1];
+        G[o + 2 * plane] = (int16_t)v[2];
+        W[(long long)y * wp + x] = w;
+    }
+}
+
+void launch_warp_tiles(const WorkItem* work, int n_work, const TileDev* tiles, const ImageDev* imgs, cudaStream_t st)
+{
+    if (n_work <= 0) return;
+    warp_tiles_kernel<<<n_work, 256, 0, st>>>(work, tiles, imgs);
+    ISB_COUNT_LAUNCH();
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel 2: pyrDown of both pyramids, one level
+// ------------------------------------------------------------------------------------------------
+// weight taps in OpenCV's operation order (A.5): `simd` = the 4-lane SIMD formulation, else the scalar one
+__device__ __forceinline__ float wdown_h(float r0, float r1, float r2, float r3, float r4, bool simd)
+{
+    if (simd) return __fadd_rn(__fmul_rn(r2, 6.f), __fadd_rn(__fmul_rn(__fadd_rn(r1, r3), 4.f), __fadd_rn(r0, r4)));
+    return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r2, 6.f), __fmul_rn(__fadd_rn(r1, r3), 4.f)), r0), r4);
+}
+__device__ __forceinline__ float wdown_v(float r0, float r1, float r2, float r3, float r4, bool simd)
+{
+    float v;
+    if (simd)
+        v = __fadd_rn(__fmul_rn(__fadd_rn(__fadd_rn(r1, r3), r2), 4.f), __fadd_rn(__fadd_rn(r0, r4), __fadd_rn(r2, r2)));
+    else
+        v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r2, 6.f), __fmul_rn(__fadd_rn(r1, r3), 4.f)), r0), r4);
+    return __fmul_rn(v, 1.f / 256.f);
+}
+
+__global__ void __launch_bounds__(256) pyrdown_tiles_kernel(const WorkItem* __restrict__ work,
+                                                            const TileDev* __restrict__ tiles, int l)
+{
+    const WorkItem wi = work[blockIdx.x];
+    const TileDev& T = tiles[wi.tile];
+    const int wl = T.w >> l, hl = T.h >> l, ow = wl >> 1, oh = hl >> 1;
+    const int ox = wi.bx * kDownBlockW + (threadIdx.x & 31);
+    const int oy = wi.by * kDownBlockH + (threadIdx.x >> 5);
+    if (ox >= ow || oy >= oh) return;
+    int xs[5], ys[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        xs[i] = reflect101(2 * ox - 2 + i, wl);
+        ys[i] = reflect101(2 * oy - 2 + i, hl);
+    }
+    // 16S planes: integer 5x5 [1 4 6 4 1], (sum + 128) >> 8
+    const int gp = T.gpitch[l], gpo = T.gpitch[l + 1];
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+        const int16_t* __restrict__ src = T.G[l] + p * T.gplane[l];
+        int acc = 0;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            const int16_t* row = src + (long long)ys[j] * gp;
+            const int h = row[xs[0]] + row[xs[4]] + 4 * (row[xs[1]] + row[xs[3]]) + 6 * row[xs[2]];
+            acc += (j == 0 || j == 4) ? h : ((j == 2) ? 6 * h : 4 * h);
+        }
+        T.G[l + 1][p * T.gplane[l + 1] + (long long)oy * gpo + ox] = (int16_t)((acc + 128) >> 8);
+    }
+    // weight plane
+    int width0 = (wl - 3) / 2 + 1;
+    width0 = min(width0, ow);
+    const int simd_h_end = width0 >= 1 ? 1 + 4 * ((width0 - 1) / 4) : 0;
+    const bool simd_h = ox >= 1 && ox < simd_h_end;
+    const bool simd_v = ox < 4 * (ow / 4);
+    const float* __restrict__ ws = T.W[l];
+    const int wp = T.wpitch[l];
+    float h[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        const float* row = ws + (long long)ys[j] * wp;
+        h[j] = wdown_h(row[xs[0]], row[xs[1]], row[xs[2]], row[xs[3]], row[xs[4]], simd_h);
+    }
+    T.W[l + 1][(long long)oy * T.wpitch[l + 1] + ox] = wdown_v(h[0], h[1], h[2], h[3], h[4], simd_v);
+}
+
+void launch_pyrdown_tiles(const WorkItem* work, int n_work, const TileDev* tiles, int level, cudaStream_t st)
+{
+    if (n_work <= 0) return;
+    pyrdown_tiles_kernel<<<n_work, 256, 0, st>>>(work, tiles, level);
+    ISB_COUNT_LAUNCH();
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel 3: per destination pixel of one level
+//   lap  = sum over covering tiles (feed order) trunc16( sat16(G_l - pyrUp(G_{l+1})) * W_l )     [wraps like short +=]
+//   wsum = sum W_l                                                                                [float, feed order]
+//   v    = trunc16( lap / (wsum + 1e-5) )  ; v = sat16( pyrUp(C_{l+1}) + v )                      [collapse]
+//   level 0: mask = wsum > 1e-5 ; out = mask ? v : 0 ; out8 = sat_u8(out)
+// ------------------------------------------------------------------------------------------------
+// one pixel of cv::pyrUp(coarse)(to exactly 2x) at fine position (fx, fy): edge rule s[-1]:=s[1], s[n]:=s[n-1]
+__device__ __forceinline__ int pyrup_at(const int16_t* __restrict__ c, int pitch, int wc, int hc, int fx, int fy)
+{
+    const int cx = fx >> 1, cy = fy >> 1;
+    const int xm = cx == 0 ? (wc > 1 ? 1 : 0) : cx - 1, xp = cx == wc - 1 ? cx : cx + 1;
+    const int ym = cy == 0 ? (hc > 1 ? 1 : 0) : cy - 1, yp = cy == hc - 1 ? cy : cy + 1;
+    const int wx0 = (fx & 1) ? 0 : 1, wx1 = (fx & 1) ? 4 : 6, wx2 = (fx & 1) ? 4 : 1;
+    const int wy0 = (fy & 1) ? 0 : 1, wy1 = (fy & 1) ? 4 : 6, wy2 = (fy & 1) ? 4 : 1;
+    const int16_t* r0 = c + (long long)ym * pitch;
+    const int16_t* r1 = c + (long long)cy * pitch;
+    const int16_t* r2 = c + (long long)yp * pitch;
+    const int h0 = wx0 * r0[xm] + wx1 * r0[cx] + wx2 * r0[xp];
+    const int h1 = wx0 * r1[xm] + wx1 * r1[cx] + wx2 * r1[xp];
+    const int h2 = wx0 * r2[xm] + wx1 * r2[cx] + wx2 * r2[xp];
+    return sat_s16((wy0 * h0 + wy1 * h1 + wy2 * h2 + 32) >> 6);
+}
+
+__global__ void __launch_bounds__(256) blend_level_kernel(DstDev D, const TileDev* __restrict__ tiles, int l, OutDev O)
+{
+    const int pw = D.pw >> l, ph = D.ph >> l;
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    // only level 0 is restricted to the rows this process owns; coarser levels cover the whole (sub-)panorama
+    const int y = (l == 0 ? D.row0 : 0) + blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= pw || y >= (l == 0 ? min(ph, D.row1) : ph)) return;
+    const int sh = D.nb - l;
+    const int cell = (y >> sh) * D.cells_x + (x >> sh);
+    int acc0 = 0, acc1 = 0, acc2 = 0;
+    float wsum = 0.f;
+    const int e1 = D.cell_start[cell + 1];
+    for (int e = D.cell_start[cell]; e < e1; ++e) {
+        const TileDev& T = tiles[D.cell_tiles[e]];
+        const int lx = x - (T.x0 >> l), ly = y - (T.y0 >> l);
+        const float w = T.W[l][(long long)ly * T.wpitch[l] + lx];
+        if (w != 0.f) {
+            const long long o = (long long)ly * T.gpitch[l] + lx;
+            const int16_t* g = T.G[l] + o;
+            int v0 = g[0], v1 = g[T.gplane[l]], v2 = g[2 * T.gplane[l]];
+            if (l < D.nb) {
+                const int wc = T.w >> (l + 1), hc = T.h >> (l + 1), cp = T.gpitch[l + 1];
+                const int16_t* c = T.G[l + 1];
+                v0 = sat_s16(v0 - pyrup_at(c, cp, wc, hc, lx, ly));
+                v1 = sat_s16(v1 - pyrup_at(c + T.gplane[l + 1], cp, wc, hc, lx, ly));
+                v2 = sat_s16(v2 - pyrup_at(c + 2 * T.gplane[l + 1], cp, wc, hc, lx, ly));
+            }
+            acc0 += trunc_s16(__fmul_rn((float)v0, w));
+            acc1 += trunc_s16(__fmul_rn((float)v1, w));
+            acc2 += trunc_s16(__fmul_rn((float)v2, w));
+            wsum = __fadd_rn(wsum, w);
+        }
+    }
+    const float den = __fadd_rn(wsum, 1e-5f);
+    int r0 = trunc_s16(__fdiv_rn((float)(short)acc0, den));
+    int r1 = trunc_s16(__fdiv_rn((float)(short)acc1, den));
+    int r2 = trunc_s16(__fdiv_rn((float)(short)acc2, den));
+    if (l < D.nb) {
+        const int wc = D.pw >> (l + 1), hc = D.ph >> (l + 1), cp = D.cpitch[l + 1];
+        const int16_t* c = D.C[l + 1];
+        r0 = sat_s16(pyrup_at(c, cp, wc, hc, x, y) + r0);
+        r1 = sat_s16(pyrup_at(c + D.cplane[l + 1], cp, wc, hc, x, y) + r1);
+        r2 = sat_s16(pyrup_at(c + 2 * D.cplane[l + 1], cp, wc, hc, x, y) + r2);
+    }
+    if (l > 0) {
+        int16_t* c = D.C[l] + (long long)y * D.cpitch[l] + x;
+        c[0] = (int16_t)r0;
+        c[D.cplane[l]] = (int16_t)r1;
+        c[2 * D.cplane[l]] = (int16_t)r2;
+        return;
+    }
+    if (x >= D.fw || y >= D.fh) return;
+    const bool on = wsum > 1e-5f;
+    if (!on) r0 = r1 = r2 = 0;
+    if (O.out8) {
+        uint8_t* p = O.out8 + y * O.pitch8 + x * 3;
+        p[0] = (uint8_t)sat_u8(r0); p[1] = (uint8_t)sat_u8(r1); p[2] = (uint8_t)sat_u8(r2);
+    }
+    if (O.mask) O.mask[y * O.mpitch + x] = on ? 255 : 0;
+    if (O.out16) {
+        int16_t* p = reinterpret_cast<int16_t*>(reinterpret_cast<char*>(O.out16) + y * O.pitch16) + x * 3;
+        p[0] = (int16_t)r0; p[1] = (int16_t)r1; p[2] = (int16_t)r2;
+    }
+}
+
+void launch_blend_level(const DstDev& dst, const TileDev* tiles, int level, const OutDev& out, cudaStream_t st)
+{
+    const int pw = dst.pw >> level;
+    const int y0 = level == 0 ? dst.row0 : 0, y1 = level == 0 ? min(dst.ph, dst.row1) : (dst.ph >> level);
+    if (y1 <= y0 || pw <= 0) return;
+    dim3 grid((pw + 31) / 32, (y1 - y0 + 7) / 8);
+    blend_level_kernel<<<grid, 256, 0, st>>>(dst, tiles, level, out);
+    ISB_COUNT_LAUNCH();
+}
+
+}  // namespace isb

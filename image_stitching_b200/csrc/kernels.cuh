@@ -1,0 +1,44 @@
+// kernels.cuh - launch wrappers of the sm_100a kernels (definitions in kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "device_types.hpp"
+
+namespace isb {
+
+long long launch_count(bool reset);
+
+// ---- classic per-call API ---------------------------------------------------------------------
+// RotationWarper::warp: dst(rect_h x rect_w, `ch` channels) from src via the separable-table inverse map.
+void launch_warp_generic(const ImageDev& img, int ch, int interp, int border, uint8_t* dst, long long dpitch,
+                         cudaStream_t st);
+// RotationWarper::buildMaps (maps are only ever stored for this diagnostic/parity entry point)
+void launch_build_maps(const ImageDev& img, float* xmap, float* ymap, long long pitch_bytes, cudaStream_t st);
+// BlocksGainCompensator::apply on 8UC3 in place
+void launch_gain_apply(uint8_t* img, int w, int h, long long pitch, const float* gain, int gw, int gh,
+                       const LinCoefDev* gx, const LinCoefDev* gy, cudaStream_t st);
+// dilate 3x3 (8UC1): src pitch given, dst tight
+void launch_dilate3x3(const uint8_t* src, int w, int h, long long spitch, uint8_t* dst, cudaStream_t st);
+// mask &= resize_linear_exact(dilated)
+void launch_seam_and(const uint8_t* dil, int mw, int mh, const uint32_t* mx, const uint32_t* my, uint8_t* mask, int w,
+                     int h, long long pitch, cudaStream_t st);
+// feed(): copyMakeBorder(REFLECT) of a 16SC3 image / CONSTANT of mask*(1/255) into a tile's level 0
+void launch_pack_tile(const TileDev* tile_dev, const TileDev& tile_host, const int16_t* img, long long ipitch,
+                      const uint8_t* mask, long long mpitch, cudaStream_t st);
+
+// ---- batched pyramid pipeline -----------------------------------------------------------------
+// number of valid (mask != 0) warped pixels of every image -> counts[img] (unsigned long long)
+void launch_count_valid(const ImageDev* imgs_dev, int n_img, const int* roi_w_host, const int* roi_h_host,
+                        unsigned long long* counts_dev, cudaStream_t st);
+// fused warp: level 0 (G0 16S planar, W0 f32) of every tile in `work`
+void launch_warp_tiles(const WorkItem* work, int n_work, const TileDev* tiles, const ImageDev* imgs, cudaStream_t st);
+// G[l+1], W[l+1] = pyrDown(G[l], W[l]) for every tile block in `work`
+void launch_pyrdown_tiles(const WorkItem* work, int n_work, const TileDev* tiles, int level, cudaStream_t st);
+// accumulate (image order) + normalise + collapse one level of the destination; level 0 writes the output
+void launch_blend_level(const DstDev& dst, const TileDev* tiles, int level, const OutDev& out, cudaStream_t st);
+
+// geometry of the CTA blocks the planner must use when it builds work lists
+constexpr int kWarpBlockW = 64, kWarpBlockH = 32;
+constexpr int kDownBlockW = 32, kDownBlockH = 8;  // in OUTPUT (level l+1) pixels
+
+}  // namespace isb

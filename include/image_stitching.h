@@ -1,0 +1,242 @@
+/*
+ * image_stitching.h - C ABI of the B200-native compositing path (libisb.so).
+ *
+ * The reference (a1q123456/image_stitching) has no library API: image_stitching/image_stitching.h:4-8
+ * declares nothing and the compositing path is an inline loop in main()
+ * (image_stitching/image_stitching.cpp:1086-1229) that drives OpenCV's
+ * cv::detail::RotationWarper / ExposureCompensator / MultiBandBlender virtual interfaces.
+ * This header gives that path the entry points a maintainer would bind instead: one C function
+ * per OpenCV method the loop calls (same names, argument order, units, ROI/mask conventions and
+ * assertion behaviour), plus the fused whole-loop call isb_compose().  Every function cites the
+ * reference line it replaces.
+ *
+ * Conventions
+ *  - All matrices are row-major.  K and R are 3x3 float32, exactly what the reference passes after
+ *    `cameras[i].K().convertTo(K, CV_32F)` (image_stitching.cpp:1135-1136, 1150-1151).
+ *  - Images are 8UC3 (or 8UC1 masks) interleaved HWC with a byte pitch; 16SC3 where OpenCV uses CV_16SC3.
+ *  - Every data pointer may be a HOST pointer or a CUDA DEVICE pointer; the library detects which
+ *    (cudaPointerGetAttributes).  Host data is staged through pinned buffers; device data is used in place.
+ *  - Functions return ISB_OK (0) or a negative code whose value is the OpenCV error class the reference
+ *    would have thrown (cv::Error::Code); isb_last_error() gives the message (thread-local).
+ *    No exception crosses this boundary.  Handles are not thread-safe (same as the reference's objects).
+ *  - There is no CPU fallback: without a CUDA device every compute entry point fails with
+ *    ISB_ERR_GPU_API.
+ */
+#ifndef IMAGE_STITCHING_B200_H
+#define IMAGE_STITCHING_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define ISB_API __declspec(dllexport)
+#else
+#define ISB_API __attribute__((visibility("default")))
+#endif
+
+/* ---- status codes (values follow cv::Error::Code) -------------------------------------------- */
+enum {
+    ISB_OK = 0,
+    ISB_ERR_NO_MEM = -4,          /* StsNoMem */
+    ISB_ERR_BAD_ARG = -5,         /* StsBadArg */
+    ISB_ERR_NULL_PTR = -27,       /* StsNullPtr */
+    ISB_ERR_UNMATCHED_SIZES = -209,
+    ISB_ERR_OUT_OF_RANGE = -211,
+    ISB_ERR_NOT_IMPLEMENTED = -213,
+    ISB_ERR_ASSERT = -215,        /* StsAssert: what CV_Assert raises */
+    ISB_ERR_GPU_NOT_SUPPORTED = -216,
+    ISB_ERR_GPU_API = -217,       /* GpuApiCallError */
+    ISB_ERR_IO = -2               /* StsError: file could not be opened / parsed */
+};
+
+enum { ISB_WARP_SPHERICAL = 0, ISB_WARP_CYLINDRICAL = 1 };      /* warp_type, image_stitching.cpp:64,919-971 */
+enum { ISB_INTER_NEAREST = 0, ISB_INTER_LINEAR = 1 };            /* cv::INTER_NEAREST / cv::INTER_LINEAR */
+enum { ISB_BORDER_CONSTANT = 0, ISB_BORDER_REFLECT = 2 };        /* cv::BORDER_CONSTANT / cv::BORDER_REFLECT */
+enum { ISB_EULER_XYZ = 0, ISB_EULER_YXZ, ISB_EULER_ZXY, ISB_EULER_ZYX, ISB_EULER_YZX, ISB_EULER_XZY }; /* euler_order.h:3-11 */
+
+ISB_API const char* isb_last_error(void);
+ISB_API const char* isb_version(void);
+/* number of CUDA devices visible (0 => every compute call fails loudly) */
+ISB_API int isb_device_count(void);
+/* stream all subsequent work of the calling thread's handles is enqueued on (cudaStream_t; NULL = default stream) */
+ISB_API int isb_set_stream(void* cuda_stream);
+/* counts kernel launches made by this library since the last reset (bench.py's `gpu_launches`) */
+ISB_API long long isb_launch_count(int reset);
+
+/* ============================================================================================
+ * Camera types and host helpers (quaternion.h, euler.h, serializer.cpp)
+ * ============================================================================================ */
+
+/* cv::detail::CameraParams as the compositing loop uses it (image_stitching.cpp:1123-1136). */
+typedef struct isb_camera {
+    double focal, aspect, ppx, ppy;
+    float R[9]; /* CV_32F after image_stitching.cpp:626-638 */
+    float t[3];
+} isb_camera;
+
+/* CameraParams::K() converted to CV_32F: [[focal,0,ppx],[0,focal*aspect,ppy],[0,0,1]] */
+ISB_API void isb_camera_K(const isb_camera* cam, float K[9]);
+
+/* Quaternion<double> members the reference uses (quaternion.h:260-322, 564-596, 172-239, 241-258, 464-478, 480-544).
+ * q = (x, y, z, w). */
+ISB_API void isb_quat_from_rotation_matrix(const double R[9], double q[4]);
+ISB_API void isb_quat_to_rotation_matrix(const double q[4], double R[9]);
+ISB_API void isb_quat_from_euler(const double euler_xyz[3], int order, double q[4]);
+ISB_API void isb_quat_from_axis_angle(const double axis[3], double angle, double q[4]);
+ISB_API void isb_quat_multiply(const double a[4], const double b[4], double out[4]);
+ISB_API void isb_quat_slerp(const double a[4], const double b[4], double t, double out[4]);
+/* the reference's EXIF pose fix-up (image_stitching.cpp:485-517): R3x3 -> quaternion -> component flips
+ * (portrait: (y,x,-z,w); landscape: (-x,y,-z,w)) -> rotation matrix */
+ISB_API void isb_pose_from_cam_transform(const double R_in[9], int is_portrait, double R_out[9]);
+
+/* euler.h:4-133 / :135-300 (double) */
+ISB_API int isb_rotation_matrix_to_euler(const double R[9], int order, double euler_xyz[3]);
+ISB_API int isb_euler_to_rotation_matrix(const double euler_xyz[3], int order, double R[9]);
+
+/* serializer.cpp.  Matrices come back as float (deserializeMatrix yields CV_32F, :69-111) or
+ * double (parseMatrixStr yields CV_64F square, :22-36). */
+ISB_API int isb_parse_matrix_str(const char* s, double* out, int capacity, int* side);
+ISB_API int isb_serialize_matrix(const double* m, int rows, int cols, int is_f32, char* buf, size_t cap);
+ISB_API int isb_deserialize_matrix(const char* s, float* out, int capacity, int* rows, int* cols);
+/* cams.data (serializer.cpp:113-167) and indices.data (:169-193); path NULL => "./cams.data" / "./indices.data" */
+ISB_API int isb_save_cams(const char* path, const isb_camera* cams, int n);
+ISB_API int isb_load_cams(const char* path, isb_camera* cams, int capacity, int* n);
+ISB_API int isb_save_indices(const char* path, const int* idx, int n);
+ISB_API int isb_load_indices(const char* path, int* idx, int capacity, int* n);
+
+/* ============================================================================================
+ * cv::detail::RotationWarper  (created by WarperCreator::create(scale), image_stitching.cpp:973,1117)
+ * ============================================================================================ */
+typedef struct isb_warper isb_warper;
+
+ISB_API isb_warper* isb_warper_create(int kind, float scale);
+ISB_API void isb_warper_destroy(isb_warper* w);
+ISB_API float isb_warper_get_scale(const isb_warper* w);
+ISB_API int isb_warper_set_scale(isb_warper* w, float scale);
+
+/* Rect roi = warper->warpRoi(sz, K, R)  (image_stitching.cpp:1138) -> rect = {x, y, width, height} */
+ISB_API int isb_warper_warp_roi(isb_warper* w, int src_w, int src_h, const float K[9], const float R[9], int rect_xywh[4]);
+/* Point2f warpPoint(pt, K, R) / warpPointBackward(pt, K, R) */
+ISB_API int isb_warper_warp_point(isb_warper* w, const float pt[2], const float K[9], const float R[9], float out[2]);
+ISB_API int isb_warper_warp_point_backward(isb_warper* w, const float pt[2], const float K[9], const float R[9], float out[2]);
+/* Rect buildMaps(src_size, K, R, xmap, ymap): xmap/ymap are rect.height x rect.width float32 with the given
+ * pitch in BYTES, computed by the same device code the fused warp uses (there the maps are never stored). */
+ISB_API int isb_warper_build_maps(isb_warper* w, int src_w, int src_h, const float K[9], const float R[9],
+                                  float* xmap, float* ymap, size_t pitch_bytes, int rect_xywh[4]);
+/* Point warp(src, K, R, interp_mode, border_mode, dst)  (image_stitching.cpp:1154,1159,985,988).
+ * src: 8UC1 or 8UC3 (channels = 1|3).  dst must hold rect.height rows of rect.width px (rect from
+ * isb_warper_warp_roi).  Supported (what the reference calls): INTER_LINEAR+BORDER_REFLECT,
+ * INTER_NEAREST+BORDER_CONSTANT, and the two cross combinations. */
+ISB_API int isb_warper_warp(isb_warper* w, const uint8_t* src, int src_w, int src_h, int channels, size_t src_pitch,
+                            const float K[9], const float R[9], int interp_mode, int border_mode, uint8_t* dst,
+                            size_t dst_pitch, int corner_xy[2]);
+
+/* ============================================================================================
+ * cv::detail::BlocksGainCompensator - apply side only  (image_stitching.cpp:1162).
+ * feed() (gain estimation) stays on the reference CPU path; its result enters through set_mat_gains
+ * (== ExposureCompensator::setMatGains).
+ * ============================================================================================ */
+typedef struct isb_compensator isb_compensator;
+
+ISB_API isb_compensator* isb_compensator_create(int block_w, int block_h);
+ISB_API void isb_compensator_destroy(isb_compensator* c);
+ISB_API int isb_compensator_set_mat_gains(isb_compensator* c, int n, const float* const* gains, const int* gain_w,
+                                          const int* gain_h);
+ISB_API int isb_compensator_get_mat_gain(const isb_compensator* c, int index, float* out, int capacity, int* gain_w, int* gain_h);
+/* compensator->apply(index, corner, image, mask): image 8UC3 in place; mask is accepted and ignored, as OpenCV does */
+ISB_API int isb_compensator_apply(isb_compensator* c, int index, const int corner_xy[2], uint8_t* image, int w, int h,
+                                  size_t pitch, const uint8_t* mask, size_t mask_pitch);
+
+/* ============================================================================================
+ * Seam-mask preparation of the loop: dilate(3x3) -> resize(INTER_LINEAR_EXACT) -> AND
+ * (image_stitching.cpp:1169-1171).  mask_warped (w x h) is updated in place.
+ * ============================================================================================ */
+ISB_API int isb_seam_mask_apply(const uint8_t* seam_mask, int seam_w, int seam_h, size_t seam_pitch,
+                                uint8_t* mask_warped, int w, int h, size_t pitch);
+
+/* ============================================================================================
+ * cv::detail::MultiBandBlender  (image_stitching.cpp:1173-1225)
+ * ============================================================================================ */
+typedef struct isb_blender isb_blender;
+
+/* Rect resultRoi(corners, sizes)  (image_stitching.cpp:1176) */
+ISB_API int isb_result_roi(const int* corners_xy, const int* sizes_wh, int n, int rect_xywh[4]);
+/* the reference's band-count rule (image_stitching.cpp:1177-1183): returns -1 when blend_width < 1 (Blender::NO) */
+ISB_API int isb_num_bands_for(int dst_w, int dst_h, float blend_strength);
+
+ISB_API isb_blender* isb_blender_create(int num_bands); /* MultiBandBlender(try_gpu, num_bands=5, CV_32F) */
+ISB_API void isb_blender_destroy(isb_blender* b);
+ISB_API int isb_blender_set_num_bands(isb_blender* b, int num_bands);
+ISB_API int isb_blender_num_bands(const isb_blender* b);        /* the REQUESTED value, as OpenCV returns */
+ISB_API int isb_blender_actual_num_bands(const isb_blender* b); /* after prepare(): min(requested, ceil(log2(max(w,h)))) */
+/* blender->prepare(corners, sizes) == prepare(resultRoi(corners, sizes)) */
+ISB_API int isb_blender_prepare(isb_blender* b, const int* corners_xy, const int* sizes_wh, int n);
+ISB_API int isb_blender_prepare_roi(isb_blender* b, const int rect_xywh[4]);
+/* dst_roi_ (padded to 2^num_bands) and dst_roi_final_ */
+ISB_API int isb_blender_get_rois(const isb_blender* b, int padded_xywh[4], int final_xywh[4]);
+/* the rect feed() builds its pyramids on: {tl.x, tl.y, br.x, br.y} in panorama coordinates */
+ISB_API int isb_blender_tile_rect(const isb_blender* b, int w, int h, int tl_x, int tl_y, int rect_tlbr[4]);
+/* blender->feed(img CV_16SC3, mask CV_8U, tl) */
+ISB_API int isb_blender_feed(isb_blender* b, const int16_t* img, size_t img_pitch, const uint8_t* mask, size_t mask_pitch,
+                             int w, int h, int tl_x, int tl_y);
+/* blender->blend(dst, dst_mask): dst CV_16SC3 and dst_mask CV_8U of dst_roi_final_ size.  Single use per prepare(). */
+ISB_API int isb_blender_blend(isb_blender* b, int16_t* dst, size_t dst_pitch, uint8_t* dst_mask, size_t mask_pitch);
+
+/* ============================================================================================
+ * Fused path: the whole loop image_stitching.cpp:1086-1229 (warp, mask, gain, ->16S, seam mask,
+ * prepare, feed x n, blend, saturate to 8U) without materialising xmap/ymap or the intermediates.
+ * ============================================================================================ */
+typedef struct isb_image { const uint8_t* data; int width, height; size_t pitch; } isb_image;   /* 8UC3 */
+typedef struct isb_gainmap { const float* data; int width, height; } isb_gainmap;                /* f32 grid; data NULL = no gain */
+typedef struct isb_mask { const uint8_t* data; int width, height; size_t pitch; } isb_mask;      /* 8UC1 seam mask; data NULL = all 255 */
+
+typedef struct isb_config {
+    int warp_kind;            /* ISB_WARP_*  (warp_type, image_stitching.cpp:64) */
+    float warped_image_scale; /* warper scale (image_stitching.cpp:1116-1117) */
+    int num_bands;            /* MultiBandBlender::setNumBands (image_stitching.cpp:1183) */
+    int strip_index;          /* this process's strip, 0 <= strip_index < strip_count */
+    int strip_count;          /* 1 = whole panorama on this GPU */
+    int cache_plan;           /* !=0: keep geometry (ROIs, trig tables, tile lists) across calls with equal cameras */
+    int reserved[8];
+} isb_config;
+
+/* Output of isb_compose: the panorama (dst_roi_final_ size).  data/mask describe the FULL panorama buffer
+ * (host, device or a peer-mapped device pointer); a strip-sharded call writes only rows
+ * [strip_y0, strip_y1) of it.  data16 (CV_16SC3, what blend() returns) is optional. */
+typedef struct isb_pano {
+    uint8_t* data;  size_t pitch;       /* 8UC3 saturated (imwrite, image_stitching.cpp:1228) */
+    uint8_t* mask;  size_t mask_pitch;  /* result_mask */
+    int16_t* data16; size_t pitch16;    /* may be NULL */
+    int roi_xywh[4];                    /* out: dst_roi_final_ */
+    int strip_y0, strip_y1;             /* out: rows of the panorama this call produced */
+} isb_pano;
+
+typedef struct isb_composer isb_composer;
+ISB_API isb_composer* isb_composer_create(const isb_config* cfg);
+ISB_API void isb_composer_destroy(isb_composer* c);
+/* Geometry pass of the first loop iteration (image_stitching.cpp:1116-1141 + :1176): corners[i], sizes[i], resultRoi. */
+ISB_API int isb_composer_plan(isb_composer* c, const isb_camera* cams, const int* src_sizes_wh, int n,
+                              int* corners_xy, int* sizes_wh, int dst_roi_xywh[4]);
+/* Runs the loop on the planned geometry. gains / seam_masks may be NULL. */
+ISB_API int isb_composer_run(isb_composer* c, const isb_image* imgs, const isb_gainmap* gains, const isb_mask* seam_masks,
+                             int n, isb_pano* out);
+/* device time (ms) of the last run split by stage; names via isb_composer_stage_name; returns #stages */
+ISB_API int isb_composer_last_timings(isb_composer* c, float* ms, int capacity);
+ISB_API const char* isb_composer_stage_name(int stage);
+/* algorithmic byte model of SURVEY.md 8(d) for the planned rig: S, M (valid warped px, counted on the device), A_p, B_alg */
+ISB_API int isb_composer_byte_model(isb_composer* c, double* S_px, double* M_px, double* Ap_px, double* B_alg_bytes);
+/* one-shot convenience == create + plan + run + destroy */
+ISB_API int isb_compose(const isb_image* imgs, const isb_camera* cams, const isb_gainmap* gains, const isb_mask* seam_masks,
+                        int n, const isb_config* cfg, isb_pano* out);
+
+/* Strip planner (multi-GPU): rows [y0,y1) of the padded panorama owned by strip i of n, boundaries on the 2^nb grid */
+ISB_API int isb_strip_rows(int padded_h, int final_h, int num_bands, int strip_index, int strip_count, int* y0, int* y1);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IMAGE_STITCHING_B200_H */

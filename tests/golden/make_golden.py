@@ -1,0 +1,73 @@
+"""Generates tests/golden/*.npz from OpenCV itself (cv2 4.13.0, IPP off) - the code the reference's
+compositing loop executes.  Run from the repo root in the build container:
+
+    python tests/golden/make_golden.py
+
+Inputs are NOT stored: they are regenerated from image_stitching_b200/synth.py (integer-only, seeded).
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import cv2  # noqa: E402
+
+from conftest import make_case  # noqa: E402
+from image_stitching_b200 import synth  # noqa: E402
+from oracle import cv_reference as cvr  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+CASES = {
+    # name: (rig, div, nb, max_images, kind)
+    "cfg2_d16_nb3": ("cfg2", 16, 3, None, "texture"),
+    "cfg2_d16_nb5_checker": ("cfg2", 16, 5, None, "checker"),
+    "cfg4_d8_nb5": ("cfg4", 8, 5, None, "texture"),
+    "cfg3_d32_nb4": ("cfg3", 32, 4, None, "texture"),
+}
+
+
+def main():
+    cvr.set_parity_mode(True)
+    print("cv2", cv2.__version__)
+    for name, (rigname, div, nb, mx, kind) in CASES.items():
+        rig, imgs, gains, nb = make_case(rigname, div, nb, mx, kind)
+        seams = cvr.seam_masks_cv(rig.warp, rig.scale, rig.Ks, rig.Rs, rig.W, rig.H)
+        ref = cvr.compose_cv(imgs, rig.Ks, rig.Rs, rig.scale, rig.warp, nb, gains, seams, keep_stages=True)
+        st = ref["stages"][0]
+        np.savez_compressed(
+            os.path.join(OUT, name + ".npz"),
+            corners=np.array(ref["corners"], np.int32), sizes=np.array(ref["sizes"], np.int32),
+            dst_roi=np.array(ref["dst_roi"], np.int32), result16=ref["result16"], mask=ref["mask"],
+            seam_sizes=np.array([s.shape for s in seams], np.int32),
+            seam_sums=np.array([int(s.astype(np.int64).sum()) for s in seams], np.int64),
+            seam0=seams[0], warped0=st["img_warped"], valid0=st["valid"], mask0=st["mask"],
+            cv2_version=np.array(cv2.__version__))
+        print(name, ref["dst_roi"], "covered", float((ref["mask"] > 0).mean()))
+    # primitive vectors: pyramids on odd shapes (weights exercise the SIMD/scalar op-order rule)
+    rng = np.random.default_rng(42)
+    prim = {}
+    for i, (h, w) in enumerate([(37, 53), (64, 96), (5, 131)]):
+        a = rng.integers(-300, 600, (h, w, 3)).astype(np.int16)
+        f = (rng.random((h, w)) * (rng.random((h, w)) > 0.3)).astype(np.float32)
+        prim[f"p16_{i}"] = a
+        prim[f"down16_{i}"] = cv2.pyrDown(a)
+        prim[f"up16_{i}"] = cv2.pyrUp(a)
+        prim[f"w_{i}"] = f
+        prim[f"downw_{i}"] = cv2.pyrDown(f)
+    m = rng.integers(0, 256, (33, 57)).astype(np.uint8)
+    prim["mask"] = m
+    prim["mask_dil"] = cv2.dilate(m, None)
+    prim["mask_up"] = cv2.resize(prim["mask_dil"], (453, 260), interpolation=cv2.INTER_LINEAR_EXACT)
+    g = synth.make_gains(1)[0]
+    prim["gain"] = g
+    prim["gain_up"] = cv2.resize(g, (451, 353), interpolation=cv2.INTER_LINEAR)
+    np.savez_compressed(os.path.join(OUT, "primitives.npz"), **prim)
+    print("primitives written")
+
+
+if __name__ == "__main__":
+    main()

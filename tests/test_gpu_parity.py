@@ -1,0 +1,241 @@
+"""GPU: the CUDA path, called through the C ABI, against the oracle (C restatement), live cv2 where present,
+and the committed golden vectors.  Bars (BASELINE.json north_star): integer ROI/corner/mask geometry
+bit-exact; 8-bit pixels max|d| <= 1 and PSNR >= 50 dB.  Most stages are in fact bit-exact and are tested so."""
+import os
+
+import numpy as np
+import pytest
+from conftest import make_case, psnr, seam_masks_oracle
+
+import image_stitching_b200 as isb
+from image_stitching_b200 import synth
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+MAX_ABS = 1       # north_star tolerance on 8-bit output
+MIN_PSNR = 50.0   # dB
+
+
+def _cams(seed, n, W, H):
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n):
+        f = float(rng.uniform(0.5, 2.5) * W)
+        K = np.array([[f, 0, W / 2 + rng.uniform(-9, 9)], [0, f * rng.uniform(0.95, 1.05), H / 2 + rng.uniform(-9, 9)],
+                      [0, 0, 1]], np.float32)
+        e = rng.uniform(-np.pi, np.pi, 3) * np.array([0.45, 1.0, 0.2])
+        out.append((K, synth.euler_yxz_to_R(*e).astype(np.float32), np.float32(f * rng.uniform(0.6, 1.4))))
+    return out
+
+
+def test_device_present_and_native_library_loaded():
+    assert isb.device_count() > 0, "GPU tests need a CUDA device: there is no CPU fallback"
+    assert b"sm_100a" in isb.lib().isb_version()
+
+
+@pytest.mark.parametrize("kind", ["spherical", "cylindrical"])
+def test_build_maps_bit_exact(kind):
+    W, H = 300, 200
+    for K, R, scale in _cams(21, 6, W, H):
+        w = isb.RotationWarper(kind, scale)
+        roi = w.warpRoi((W, H), K, R)
+        if roi[2] * roi[3] > 6e6:
+            continue
+        r2, xm, ym = w.buildMaps((W, H), K, R)
+        r3, xo, yo = orc.build_maps(kind, scale, W, H, K, R)
+        assert r2 == r3 == roi
+        assert np.array_equal(xm.view(np.int32), xo.view(np.int32))
+        assert np.array_equal(ym.view(np.int32), yo.view(np.int32))
+
+
+@pytest.mark.parametrize("kind", ["spherical", "cylindrical"])
+@pytest.mark.parametrize("content", ["texture", "checker"])
+def test_warp_bit_exact(kind, content):
+    W, H = 280, 190
+    img = synth.make_image(2, W, H, content)
+    msk = np.full((H, W), 255, np.uint8)
+    for K, R, scale in _cams(22, 5, W, H):
+        w = isb.RotationWarper(kind, scale)
+        if np.prod(w.warpRoi((W, H), K, R)[2:]) > 5e6:
+            continue
+        c1, a = w.warp(img, K, R, isb.INTER_LINEAR, isb.BORDER_REFLECT)
+        c2, b = orc.warp(kind, scale, img, K, R, orc.LINEAR, 1)
+        assert c1 == c2 and np.array_equal(a, b)
+        c1, a = w.warp(msk, K, R, isb.INTER_NEAREST, isb.BORDER_CONSTANT)
+        c2, b = orc.warp(kind, scale, msk, K, R, orc.NEAREST, 0)
+        assert c1 == c2 and np.array_equal(a, b)
+        # the cross combinations the warper interface also allows
+        _, a = w.warp(img, K, R, isb.INTER_LINEAR, isb.BORDER_CONSTANT)
+        _, b = orc.warp(kind, scale, img, K, R, orc.LINEAR, 0)
+        assert np.array_equal(a, b)
+        _, a = w.warp(img[:, :, 0].copy(), K, R, isb.INTER_NEAREST, isb.BORDER_REFLECT)
+        _, b = orc.warp(kind, scale, img[:, :, 0].copy(), K, R, orc.NEAREST, 1)
+        assert np.array_equal(a, b)
+
+
+def test_wrap_around_and_pole_images():
+    rig = synth.make_rig("cfg2", 16)
+    img = synth.make_image(0, rig.W, rig.H)
+    w = isb.RotationWarper("spherical", rig.scale)
+    c1, a = w.warp(img, rig.Ks[0], rig.Rs[0], isb.INTER_LINEAR, isb.BORDER_REFLECT)  # straddles u = +-pi*scale
+    c2, b = orc.warp("spherical", rig.scale, img, rig.Ks[0], rig.Rs[0], orc.LINEAR, 1)
+    assert a.shape[1] > 4 * rig.W and c1 == c2 and np.array_equal(a, b)
+    R = synth.euler_yxz_to_R(-1.45, 0.4, 0.02).astype(np.float32)  # looks at a pole
+    c1, a = w.warp(img, rig.Ks[0], R, isb.INTER_LINEAR, isb.BORDER_REFLECT)
+    c2, b = orc.warp("spherical", rig.scale, img, rig.Ks[0], R, orc.LINEAR, 1)
+    assert c1 == c2 and np.array_equal(a, b)
+
+
+def test_gain_apply_and_seam_mask():
+    img = synth.make_image(1, 451, 353)
+    gains = synth.make_gains(3)
+    comp = isb.BlocksGainCompensator(64, 64, 1)
+    comp.setMatGains(gains)
+    assert np.array_equal(comp.getMatGain(2), gains[2])
+    for i in range(3):
+        assert np.array_equal(comp.apply(i, (0, 0), img), orc.gain_apply(img, gains[i]))
+    with pytest.raises(isb.IsbError):
+        comp.apply(7, (0, 0), img)
+    p = np.load(os.path.join(GOLD, "primitives.npz"))
+    valid = np.full((260, 453), 255, np.uint8)
+    valid[:, :40] = 0
+    assert np.array_equal(isb.seam_mask_apply(p["mask"], valid), p["mask_up"] & valid)
+    rng = np.random.default_rng(4)
+    for (sw, sh, dw, dh) in [(41, 29, 327, 233), (7, 5, 50, 41), (100, 1, 333, 1), (1, 9, 5, 77)]:
+        m = rng.integers(0, 256, (sh, sw)).astype(np.uint8)
+        v = rng.integers(0, 2, (dh, dw)).astype(np.uint8) * 255
+        assert np.array_equal(isb.seam_mask_apply(m, v), orc.resize_linear_exact(orc.dilate3x3(m), dw, dh) & v)
+
+
+@pytest.mark.parametrize("nb", [0, 1, 3, 5, 12])
+def test_blender_feed_blend_bit_exact(nb):
+    rng = np.random.default_rng(nb)
+    corners = [(0, 0), (150, -30), (-77, 41), (-60, -20)]
+    sizes = [(300, 200), (257, 213), (190, 260), (31, 17)]
+    a, b = isb.MultiBandBlender(0, nb), orc.Blender(nb)
+    a.prepare(corners, sizes)
+    b.prepare(orc.result_roi(corners, sizes))
+    for (cx, cy), (sw, sh) in zip(corners, sizes):
+        img = rng.integers(-50, 300, (sh, sw, 3)).astype(np.int16)
+        m = np.zeros((sh, sw), np.uint8)
+        m[3:-3, 3:-3] = 255
+        m[5:12, 4:20] = rng.integers(0, 256, (7, 16))  # grey seam-edge weights
+        a.feed(img, m, (cx, cy))
+        b.feed(img, m, (cx, cy))
+    r1, m1 = a.blend()
+    r2, m2 = b.blend()
+    assert np.array_equal(m1, m2)
+    assert np.array_equal(r1, r2)
+
+
+def test_blender_contract_errors():
+    b = isb.MultiBandBlender(0, 3)
+    with pytest.raises(isb.IsbError):  # feed before prepare
+        b.feed(np.zeros((8, 8, 3), np.int16), np.zeros((8, 8), np.uint8), (0, 0))
+    b.prepare((0, 0, 64, 64))
+    with pytest.raises(isb.IsbError):  # img must be CV_16SC3 (blenders.cpp:365)
+        b.feed(np.zeros((8, 8, 3), np.float32), np.zeros((8, 8), np.uint8), (0, 0))
+    with pytest.raises(isb.IsbError):  # mask must be CV_8U (blenders.cpp:366)
+        b.feed(np.zeros((8, 8, 3), np.int16), np.zeros((8, 8), np.float32), (0, 0))
+    # an image-less blend gives an all-zero panorama and mask
+    r, m = b.blend()
+    assert r.shape == (64, 64, 3) and not r.any() and not m.any()
+    with pytest.raises(isb.IsbError):  # single use per prepare()
+        b.blend()
+    w = isb.RotationWarper("spherical", 10.0)
+    with pytest.raises(isb.IsbError):
+        isb.RotationWarper("fisheye", 10.0)
+    with pytest.raises(isb.IsbError):
+        w.warpRoi((0, 10), np.eye(3), np.eye(3))
+
+
+def _check(out, ref, exact16=True):
+    assert out["corners"] == ref["corners"] and out["sizes"] == ref["sizes"] and tuple(out["dst_roi"]) == tuple(ref["dst_roi"])
+    assert np.array_equal(out["mask"], ref["mask"])  # integer mask geometry: bit-exact
+    r8 = np.clip(ref["result16"], 0, 255).astype(np.uint8)
+    d = np.abs(out["result8"].astype(int) - r8.astype(int))
+    assert d.max() <= MAX_ABS, int(d.max())
+    assert psnr(out["result8"], r8) >= MIN_PSNR
+    if exact16:
+        assert np.array_equal(out["result16"], ref["result16"])
+
+
+@pytest.mark.parametrize("case", [("cfg2", 8, 5, "texture"), ("cfg2", 16, 3, "checker"), ("cfg4", 8, 5, "texture"),
+                                  ("cfg3", 16, 4, "texture"), ("cfg5", 16, 4, "texture")])
+def test_compose_vs_oracle(case):
+    name, div, nb, kind = case
+    rig, imgs, gains, nb = make_case(name, div, nb, max_images=14, kind=kind)
+    seams = seam_masks_oracle(rig)
+    ref = orc.compose(imgs, rig.Ks, rig.Rs, rig.scale, rig.warp, nb, gains, seams)
+    out = isb.compose(imgs, rig.Ks, rig.Rs, rig.scale, rig.warp, nb, gains, seams)
+    _check(out, ref)
+    # no gains / no seam masks (both optional in the loop)
+    ref = orc.compose(imgs[:3], rig.Ks[:3], rig.Rs[:3], rig.scale, rig.warp, nb)
+    out = isb.compose(imgs[:3], rig.Ks[:3], rig.Rs[:3], rig.scale, rig.warp, nb)
+    _check(out, ref)
+
+
+@pytest.mark.parametrize("name", ["cfg2_d16_nb3", "cfg2_d16_nb5_checker", "cfg4_d8_nb5", "cfg3_d32_nb4"])
+def test_compose_vs_golden(name):
+    cases = {"cfg2_d16_nb3": ("cfg2", 16, 3, "texture"), "cfg2_d16_nb5_checker": ("cfg2", 16, 5, "checker"),
+             "cfg4_d8_nb5": ("cfg4", 8, 5, "texture"), "cfg3_d32_nb4": ("cfg3", 32, 4, "texture")}
+    rigname, div, nb, kind = cases[name]
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    rig, imgs, gains, nb = make_case(rigname, div, nb, kind=kind)
+    # seam masks through OUR warper at seam scale - must reproduce cv2's
+    src = synth.seam_source_mask(rig.W, rig.H)
+    seams = []
+    for K, R in zip(rig.Ks, rig.Rs):
+        Ks, ss = synth.seam_camera(K, rig.scale)
+        seams.append(isb.RotationWarper(rig.warp, ss).warp(src, Ks, R, isb.INTER_NEAREST, isb.BORDER_CONSTANT)[1])
+    assert [s.shape for s in seams] == [tuple(v) for v in g["seam_sizes"]]
+    assert np.array_equal(seams[0], g["seam0"])
+    out = isb.compose(imgs, rig.Ks, rig.Rs, rig.scale, rig.warp, nb, gains, seams)
+    ref = dict(corners=[tuple(v) for v in g["corners"]], sizes=[tuple(v) for v in g["sizes"]], dst_roi=tuple(g["dst_roi"]),
+               mask=g["mask"], result16=g["result16"])
+    _check(out, ref)
+
+
+def test_compose_with_device_pointers_and_plan_cache():
+    torch = pytest.importorskip("torch")
+    rig, imgs, gains, nb = make_case("cfg2", 16, 4)
+    seams = seam_masks_oracle(rig)
+    ref = orc.compose(imgs, rig.Ks, rig.Rs, rig.scale, rig.warp, nb, gains, seams)
+    c = isb.Composer(rig.warp, rig.scale, nb, cache_plan=True)
+    c.plan(isb.cameras_from_KR(rig.Ks, rig.Rs), [(rig.W, rig.H)] * rig.n)
+    dimgs = [torch.from_numpy(im).cuda() for im in imgs]
+    x, y, w, h = c.dst_roi
+    o8 = torch.zeros((h, w, 3), dtype=torch.uint8, device="cuda")
+    om = torch.zeros((h, w), dtype=torch.uint8, device="cuda")
+    o16 = torch.zeros((h, w, 3), dtype=torch.int16, device="cuda")
+    for _ in range(2):  # second run reuses the cached plan and all buffers
+        c.plan(isb.cameras_from_KR(rig.Ks, rig.Rs), [(rig.W, rig.H)] * rig.n)
+        c.run(dimgs, gains, seams, out=o8, out_mask=om, out16=o16)
+        torch.cuda.synchronize()
+        _check(dict(corners=c.corners, sizes=c.sizes, dst_roi=c.dst_roi, mask=om.cpu().numpy(), result8=o8.cpu().numpy(),
+                    result16=o16.cpu().numpy()), ref)
+    t = c.timings()
+    assert set(t) == {"h2d", "warp", "pyrdown", "blend", "d2h"} and t["warp"] > 0
+    bm = c.byte_model()
+    valid = sum(int((orc.warp(rig.warp, rig.scale, np.full((rig.H, rig.W), 255, np.uint8), K, R, orc.NEAREST, 0)[1] > 0).sum())
+                for K, R in zip(rig.Ks, rig.Rs))
+    assert bm["M"] == valid and bm["S"] == rig.n * rig.W * rig.H and bm["Ap"] == w * h
+
+
+@pytest.mark.parametrize("strips", [2, 3, 8])
+def test_strip_sharding_is_bit_exact(strips):
+    """N logical strips on one GPU reproduce the unsharded panorama bit for bit."""
+    rig, imgs, gains, nb = make_case("cfg3", 16, 3)
+    seams = seam_masks_oracle(rig)
+    full = isb.compose(imgs, rig.Ks, rig.Rs, rig.scale, rig.warp, nb, gains, seams)
+    h, w = full["mask"].shape
+    out8, outm, out16 = np.zeros((h, w, 3), np.uint8), np.zeros((h, w), np.uint8), np.zeros((h, w, 3), np.int16)
+    rows = []
+    for i in range(strips):
+        c = isb.Composer(rig.warp, rig.scale, nb, strip_index=i, strip_count=strips)
+        c.plan(isb.cameras_from_KR(rig.Ks, rig.Rs), [(rig.W, rig.H)] * rig.n)
+        r = c.run(imgs, gains, seams, out=out8, out_mask=outm, out16=out16)
+        rows.append(r["strip_rows"])
+    assert rows[0][0] == 0 and rows[-1][1] == h and all(a[1] == b[0] for a, b in zip(rows, rows[1:]))
+    assert np.array_equal(outm, full["mask"]) and np.array_equal(out16, full["result16"]) and np.array_equal(out8, full["result8"])

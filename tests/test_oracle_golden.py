@@ -1,0 +1,59 @@
+"""CPU: the C oracle (oracle/isb_oracle.c) against the cv2-generated golden vectors in tests/golden/."""
+import os
+
+import numpy as np
+import pytest
+from conftest import make_case, seam_masks_oracle
+
+from oracle import oracle as orc
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+CASES = {
+    "cfg2_d16_nb3": ("cfg2", 16, 3, None, "texture"),
+    "cfg2_d16_nb5_checker": ("cfg2", 16, 5, None, "checker"),
+    "cfg4_d8_nb5": ("cfg4", 8, 5, None, "texture"),
+    "cfg3_d32_nb4": ("cfg3", 32, 4, None, "texture"),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_compose_matches_golden(name):
+    rigname, div, nb, mx, kind = CASES[name]
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    rig, imgs, gains, nb = make_case(rigname, div, nb, mx, kind)
+    seams = seam_masks_oracle(rig)
+    # the oracle's own nearest warp reproduces the cv2 seam masks
+    assert [s.shape for s in seams] == [tuple(v) for v in g["seam_sizes"]]
+    assert [int(s.astype(np.int64).sum()) for s in seams] == [int(v) for v in g["seam_sums"]]
+    assert np.array_equal(seams[0], g["seam0"])
+    out = orc.compose(imgs, rig.Ks, rig.Rs, rig.scale, rig.warp, nb, gains, seams)
+    assert out["corners"] == [tuple(v) for v in g["corners"]]
+    assert out["sizes"] == [tuple(v) for v in g["sizes"]]
+    assert out["dst_roi"] == tuple(g["dst_roi"])
+    assert np.array_equal(out["mask"], g["mask"])
+    assert np.array_equal(out["result16"], g["result16"])  # bit-exact, int16
+
+
+def test_stage_vectors():
+    g = np.load(os.path.join(GOLD, "cfg2_d16_nb3.npz"))
+    rig, imgs, gains, nb = make_case("cfg2", 16, 3)
+    _, iw = orc.warp(rig.warp, rig.scale, imgs[0], rig.Ks[0], rig.Rs[0], orc.LINEAR, 1)
+    _, mw = orc.warp(rig.warp, rig.scale, np.full(imgs[0].shape[:2], 255, np.uint8), rig.Ks[0], rig.Rs[0], orc.NEAREST, 0)
+    assert np.array_equal(mw, g["valid0"])
+    assert np.array_equal(orc.gain_apply(iw, gains[0]), g["warped0"])
+    up = orc.resize_linear_exact(orc.dilate3x3(g["seam0"]), mw.shape[1], mw.shape[0])
+    assert np.array_equal(up & mw, g["mask0"])
+
+
+def test_primitives():
+    p = np.load(os.path.join(GOLD, "primitives.npz"))
+    for i in range(3):
+        assert np.array_equal(orc.pyrdown_16s(p[f"p16_{i}"]), p[f"down16_{i}"])
+        assert np.array_equal(orc.pyrup_16s(p[f"p16_{i}"]), p[f"up16_{i}"])
+        assert np.array_equal(orc.pyrdown_32f(p[f"w_{i}"]), p[f"downw_{i}"])  # float op order, bit-exact
+    assert np.array_equal(orc.dilate3x3(p["mask"]), p["mask_dil"])
+    assert np.array_equal(orc.resize_linear_exact(p["mask_dil"], 453, 260), p["mask_up"])
+    gu = orc.resize_linear_f32(p["gain"], 451, 353)
+    # the float gain-map upsample is the one step that is only pinned to <= 1 ulp
+    assert np.max(np.abs(gu.view(np.int32).astype(np.int64) - p["gain_up"].view(np.int32))) <= 1
+    assert np.mean(gu != p["gain_up"]) < 0.02
