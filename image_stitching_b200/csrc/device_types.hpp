@@ -37,6 +37,12 @@ struct TileDev {
     int img;                 // index into ImageDev[] (fused path) or -1 (classic feed)
     int left, top;           // ROI top-left relative to the tile origin (copyMakeBorder's left/top)
     int roi_w, roi_h;        // warped image size (tile px outside are REFLECT padding, weight 0)
+    // Level 0 of the fused path is byte-packed: one uint32 per pixel = b | g<<8 | r<<16 | m<<24, where (b,g,r) is the
+    // gain-compensated 8-bit warp result and m the 8-bit blend mask (weight = m * (1/255), exactly as feed() forms it).
+    // It replaces G[0]/W[0] (10 B/px -> 4 B/px) whenever `packed` is set; the classic feed() path keeps 16S + f32.
+    uint32_t* P0;
+    int ppitch;              // elements
+    int packed;
     int16_t* G[kMaxLevels];  // plane p at G[l] + p * gplane[l]
     float* W[kMaxLevels];
     int gpitch[kMaxLevels];  // elements
@@ -59,6 +65,7 @@ struct DstDev {
     const int* cell_start;     // CSR: tiles covering each macro cell, ascending feed order
     const int* cell_tiles;
     int row0, row1;            // level-0 rows [row0,row1) this process owns (strip)
+    int packed0;               // all tiles carry the byte-packed level 0 (fused composer)
 };
 
 struct OutDev {

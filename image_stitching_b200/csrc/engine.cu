@@ -106,20 +106,20 @@ PyramidEngine::~PyramidEngine()
     for (DevBuf* b : extra_) delete b;
 }
 
-void PyramidEngine::reset(const BlendGeometry& g, int sub_y0, int sub_h, int own_y0, int own_y1)
+void PyramidEngine::reset(const BlendGeometry& g, int sub_y0, int sub_h, int own_y0, int own_y1, bool packed)
 {
     g_ = g;
     sub_y0_ = sub_y0;
     sub_h_ = sub_h;
     own_y0_ = own_y0;
     own_y1_ = own_y1;
+    packed_ = packed;
     tiles_.clear();
-    tile_off_.clear();
     committed_ = 0;
     arena_.begin();
-    frozen_arena_ = false;
     warp_work_.clear();
     down_work_.assign(g.nb, {});
+    dst_.cell_start = nullptr;
     ISB_ASSERT(g.nb < kMaxLevels);
 }
 
@@ -127,20 +127,24 @@ int PyramidEngine::add_tile(int img_index, int w, int h, int tlx, int tly)
 {
     int tl[2], br[2];
     g_.tile_rect(w, h, tlx, tly, tl, br);
-    const int X0 = tl[0] - g_.roi.x, X1 = br[0] - g_.roi.x;
-    const int Y0 = tl[1] - g_.roi.y, Y1 = br[1] - g_.roi.y;
-    const int cy0 = std::max(Y0, sub_y0_), cy1 = std::min(Y1, sub_y0_ + sub_h_);
-    if (cy1 <= cy0 || X1 <= X0) return -1;
+    return add_rect(img_index, tl[0] - g_.roi.x, tl[1] - g_.roi.y, br[0] - tl[0], br[1] - tl[1], tlx, tly, w, h);
+}
+
+int PyramidEngine::add_rect(int img_index, int X0, int Y0, int W, int H, int tlx, int tly, int roi_w, int roi_h)
+{
+    const int cy0 = std::max(Y0, sub_y0_), cy1 = std::min(Y0 + H, sub_y0_ + sub_h_);
+    if (cy1 <= cy0 || W <= 0) return -1;
     TileDev t{};
     t.x0 = X0;
     t.y0 = cy0 - sub_y0_;
-    t.w = X1 - X0;
+    t.w = W;
     t.h = cy1 - cy0;
     t.img = img_index;
-    t.left = tlx - tl[0];
+    t.left = (tlx - g_.roi.x) - X0;
     t.top = (tly - g_.roi.y) - cy0;
-    t.roi_w = w;
-    t.roi_h = h;
+    t.roi_w = roi_w;
+    t.roi_h = roi_h;
+    t.packed = packed_ ? 1 : 0;
     tiles_.push_back(t);
     return (int)tiles_.size() - 1;
 }
@@ -154,10 +158,14 @@ void PyramidEngine::commit_tiles(cudaStream_t st)
     Arena local;
     Arena& ar = (first == 0) ? arena_ : local;
     ar.begin();
-    std::vector<size_t> goff((size_t)(end - first) * (nb + 1)), woff(goff.size());
+    std::vector<size_t> goff((size_t)(end - first) * (nb + 1)), woff(goff.size()), poff(end - first, 0);
     for (int t = first; t < end; ++t) {
         TileDev& T = tiles_[t];
-        for (int l = 0; l <= nb; ++l) {
+        if (T.packed) {
+            T.ppitch = round_up(T.w, 4);
+            poff[t - first] = ar.take((size_t)T.ppitch * T.h * sizeof(uint32_t));
+        }
+        for (int l = T.packed ? 1 : 0; l <= nb; ++l) {
             const int wl = T.w >> l, hl = T.h >> l;
             T.gpitch[l] = round_up(wl, 8);
             T.wpitch[l] = round_up(wl, 4);
@@ -173,11 +181,14 @@ void PyramidEngine::commit_tiles(cudaStream_t st)
         extra_.push_back(b);
         base = static_cast<char*>(b->ensure(local.used()));
     }
-    for (int t = first; t < end; ++t)
-        for (int l = 0; l <= nb; ++l) {
-            tiles_[t].G[l] = reinterpret_cast<int16_t*>(base + goff[(size_t)(t - first) * (nb + 1) + l]);
-            tiles_[t].W[l] = reinterpret_cast<float*>(base + woff[(size_t)(t - first) * (nb + 1) + l]);
+    for (int t = first; t < end; ++t) {
+        TileDev& T = tiles_[t];
+        if (T.packed) T.P0 = reinterpret_cast<uint32_t*>(base + poff[t - first]);
+        for (int l = T.packed ? 1 : 0; l <= nb; ++l) {
+            T.G[l] = reinterpret_cast<int16_t*>(base + goff[(size_t)(t - first) * (nb + 1) + l]);
+            T.W[l] = reinterpret_cast<float*>(base + woff[(size_t)(t - first) * (nb + 1) + l]);
         }
+    }
     // work lists for the new tiles
     warp_work_.clear();
     for (auto& v : down_work_) v.clear();
@@ -187,9 +198,11 @@ void PyramidEngine::commit_tiles(cudaStream_t st)
             for (int bx = 0; bx < (T.w + kWarpBlockW - 1) / kWarpBlockW; ++bx) warp_work_.push_back(WorkItem{t, bx, by, 0});
         for (int l = 0; l < nb; ++l) {
             const int ow = T.w >> (l + 1), oh = T.h >> (l + 1);
-            for (int by = 0; by < (oh + kDownBlockH - 1) / kDownBlockH; ++by)
-                for (int bx = 0; bx < (ow + kDownBlockW - 1) / kDownBlockW; ++bx)
-                    down_work_[l].push_back(WorkItem{t, bx, by, 0});
+            // levels with an even output width run the register-rolling kernel (64 x 128 outputs per CTA)
+            const int bw = fast_down(l) ? kFastDownCols : kDownBlockW;
+            const int bh = fast_down(l) ? kFastDownRows * kFastDownWarps : kDownBlockH;
+            for (int by = 0; by < (oh + bh - 1) / bh; ++by)
+                for (int bx = 0; bx < (ow + bw - 1) / bw; ++bx) down_work_[l].push_back(WorkItem{t, bx, by, 0});
         }
     }
     // uploads (pageable sources: the runtime stages them before returning, so the vectors may be reused)
@@ -222,8 +235,11 @@ void PyramidEngine::build_pyramids(int first, int end, cudaStream_t st)
     (void)first;
     (void)end;  // the work lists always describe the last committed batch
     const WorkItem* base = down_work_dev_.as<WorkItem>();
-    for (int l = 0; l < g_.nb; ++l)
-        launch_pyrdown_tiles(base + down_off_[l], (int)(down_off_[l + 1] - down_off_[l]), tiles_dev(), l, st);
+    for (int l = 0; l < g_.nb; ++l) {
+        const int n = (int)(down_off_[l + 1] - down_off_[l]);
+        if (fast_down(l)) launch_pyrdown_fast(base + down_off_[l], n, tiles_dev(), l, packed_ && l == 0, st);
+        else launch_pyrdown_tiles(base + down_off_[l], n, tiles_dev(), l, st);
+    }
 }
 
 void PyramidEngine::blend(const OutDev& out, cudaStream_t st)
@@ -233,6 +249,7 @@ void PyramidEngine::blend(const OutDev& out, cudaStream_t st)
         // destination pyramid (levels 1..nb) + CSR of covering tiles per macro cell
         dst_ = DstDev{};
         dst_.nb = nb;
+        dst_.packed0 = packed_ ? 1 : 0;
         dst_.pw = g_.roi.w;
         dst_.ph = sub_h_;
         dst_.fw = g_.roi_final.w;
@@ -269,7 +286,10 @@ void PyramidEngine::blend(const OutDev& out, cudaStream_t st)
         dst_.cell_start = cd;
         dst_.cell_tiles = cd + start.size();
     }
-    for (int l = nb; l >= 0; --l) launch_blend_level(dst_, tiles_dev(), l, out, st);
+    for (int l = nb; l >= 0; --l) {
+        if (l < nb) launch_blend_quad(dst_, tiles_dev(), l, out, st);
+        else launch_blend_level(dst_, tiles_dev(), l, out, st);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -483,7 +503,7 @@ void Blender::prepare(const Rect& roi)
     ISB_ASSERT(requested_ >= 0);
     BlendGeometry g;
     g.prepare(roi, requested_);
-    eng_.reset(g, 0, g.roi.h, 0, g.roi.h);
+    eng_.reset(g, 0, g.roi.h, 0, g.roi.h, /*packed=*/false);
     prepared_ = true;
 }
 
@@ -613,27 +633,22 @@ void Composer::plan(const isb_camera* cams, const int* sizes_wh, int n, int* cor
         strip_rows(g.roi.h, g.nb, cfg_.strip_index, cfg_.strip_count, y0, y1);
         const int halo = cfg_.strip_count > 1 ? 4 * (1 << g.nb) : 0;
         const int sy0 = std::max(0, y0 - halo), sy1 = std::min(g.roi.h, y1 + halo);
-        eng_.reset(g, sy0, std::max(sy1 - sy0, 0), y0, y1);
-        tile_of_image_.assign(n, -1);
-        for (int i = 0; i < n; ++i)
-            tile_of_image_[i] = eng_.add_tile(i, img_[i].roi.w, img_[i].roi.h, img_[i].roi.x, img_[i].roi.y);
-        eng_.commit_tiles(st);
-        // separable trig tables + slots for the per-run coefficient tables
+        eng_.reset(g, sy0, std::max(sy1 - sy0, 0), y0, y1, /*packed=*/true);
+
+        // separable trig tables (every image) + slots for the per-run coefficient tables
         tables_.begin();
         for (int i = 0; i < n; ++i) {
             ImagePlan& P = img_[i];
-            if (tile_of_image_[i] < 0) continue;
             P.col_off = tables_.take(P.roi.w * sizeof(F2));
             P.row_off = tables_.take(P.roi.h * sizeof(F2));
             P.gx_off = tables_.take(P.roi.w * sizeof(LinCoefDev));
             P.gy_off = tables_.take(P.roi.h * sizeof(LinCoefDev));
             P.mx_off = tables_.take(P.roi.w * sizeof(uint32_t));
             P.my_off = tables_.take(P.roi.h * sizeof(uint32_t));
+            P.gain_w = P.gain_h = P.seam_w = P.seam_h = -1;
         }
         char* tb = tables_.commit();
-        auto tabs = [&](int i) {
-            if (tile_of_image_[i] >= 0) build_trig_tables(img_[i].proj, img_[i].roi, img_[i].col, img_[i].row);
-        };
+        auto tabs = [&](int i) { build_trig_tables(img_[i].proj, img_[i].roi, img_[i].col, img_[i].row); };
         if (nthr <= 1) {
             for (int i = 0; i < n; ++i) tabs(i);
         } else {
@@ -644,10 +659,81 @@ void Composer::plan(const isb_camera* cams, const int* sizes_wh, int n, int* cor
         }
         for (int i = 0; i < n; ++i) {
             ImagePlan& P = img_[i];
-            if (tile_of_image_[i] < 0) continue;
             ISB_CUDA(cudaMemcpyAsync(tb + P.col_off, P.col.data(), P.col.size() * sizeof(F2), cudaMemcpyHostToDevice, st));
             ISB_CUDA(cudaMemcpyAsync(tb + P.row_off, P.row.data(), P.row.size() * sizeof(F2), cudaMemcpyHostToDevice, st));
         }
+
+        // Support culling.  The device marks, per macro cell (2^nb x 2^nb px) of every image's feed() tile, whether
+        // any warped pixel is valid.  Weight pyramids are exactly zero farther than 2*2^nb px from the support and the
+        // Laplacian there never reaches the output, so pyramids are only built on rectangles that cover the occupied
+        // cells dilated by 4 cells (>= the 4*2^nb px dependency radius): a wrap-around image whose ROI
+        // spans the whole panorama shrinks to its two real ends.  Rect edges that coincide with the tile's own edges
+        // keep OpenCV's border rules; the other cuts are too far from any non-zero weight to matter.
+        struct FullTile { int X0, Y0, W, H; };
+        std::vector<FullTile> full(n);
+        std::vector<OccTile> occ_tiles(n);
+        std::vector<ImageDev> idev(n);
+        size_t occ_bytes = 0;
+        int max_w = 0, max_h = 0;
+        for (int i = 0; i < n; ++i) {
+            const ImagePlan& P = img_[i];
+            int tl[2], br[2];
+            g.tile_rect(P.roi.w, P.roi.h, P.roi.x, P.roi.y, tl, br);
+            full[i] = FullTile{tl[0] - g.roi.x, tl[1] - g.roi.y, br[0] - tl[0], br[1] - tl[1]};
+            occ_tiles[i] = OccTile{i, P.roi.x - tl[0], P.roi.y - tl[1], full[i].W, full[i].H, (long long)occ_bytes};
+            occ_bytes += (size_t)(full[i].W >> g.nb) * (full[i].H >> g.nb);
+            max_w = std::max(max_w, full[i].W);
+            max_h = std::max(max_h, full[i].H);
+            ImageDev& I = idev[i];
+            I = ImageDev{};
+            I.sw = P.src_w; I.sh = P.src_h; I.roi_w = P.roi.w; I.roi_h = P.roi.h;
+            std::memcpy(I.kr, P.proj.k_rinv, sizeof(I.kr));
+            I.col = reinterpret_cast<const F2*>(tb + P.col_off);
+            I.row = reinterpret_cast<const F2*>(tb + P.row_off);
+        }
+        std::vector<uint8_t> occ(occ_bytes, 0);
+        {
+            DevBuf occ_dev, occ_tiles_dev;
+            ImageDev* idp = static_cast<ImageDev*>(imgs_dev_.ensure(n * sizeof(ImageDev)));
+            ISB_CUDA(cudaMemcpyAsync(idp, idev.data(), n * sizeof(ImageDev), cudaMemcpyHostToDevice, st));
+            OccTile* otp = static_cast<OccTile*>(occ_tiles_dev.ensure(n * sizeof(OccTile)));
+            ISB_CUDA(cudaMemcpyAsync(otp, occ_tiles.data(), n * sizeof(OccTile), cudaMemcpyHostToDevice, st));
+            uint8_t* od = static_cast<uint8_t*>(occ_dev.ensure(std::max<size_t>(occ_bytes, 1)));
+            ISB_CUDA(cudaMemsetAsync(od, 0, std::max<size_t>(occ_bytes, 1), st));
+            for (int z0 = 0; z0 < n; z0 += 32768)
+                launch_occupancy(otp + z0, std::min(32768, n - z0), max_w, max_h, idp, g.nb, od, st);
+            ISB_CUDA(cudaMemcpyAsync(occ.data(), od, occ_bytes, cudaMemcpyDeviceToHost, st));
+            ISB_CUDA(cudaStreamSynchronize(st));
+        }
+        tiles_of_image_.assign(n, {});
+        const int kDilate = 4;
+        for (int i = 0; i < n; ++i) {
+            const int cw = full[i].W >> g.nb, chh = full[i].H >> g.nb;
+            const uint8_t* o = occ.data() + occ_tiles[i].occ_off;
+            // dilated column / row extents
+            std::vector<int> col_lo(cw, INT_MAX), col_hi(cw, INT_MIN);
+            for (int cy = 0; cy < chh; ++cy)
+                for (int cx = 0; cx < cw; ++cx)
+                    if (o[(size_t)cy * cw + cx])
+                        for (int dx = std::max(0, cx - kDilate); dx <= std::min(cw - 1, cx + kDilate); ++dx) {
+                            col_lo[dx] = std::min(col_lo[dx], std::max(0, cy - kDilate));
+                            col_hi[dx] = std::max(col_hi[dx], std::min(chh - 1, cy + kDilate));
+                        }
+            for (int cx = 0; cx < cw;) {
+                if (col_hi[cx] < col_lo[cx]) { ++cx; continue; }
+                int x1 = cx, lo = col_lo[cx], hi = col_hi[cx];
+                while (x1 + 1 < cw && col_hi[x1 + 1] >= col_lo[x1 + 1]) {
+                    ++x1;
+                    lo = std::min(lo, col_lo[x1]);
+                    hi = std::max(hi, col_hi[x1]);
+                }
+                const int t = eng_.add_rect(i, full[i].X0 + (cx << g.nb), full[i].Y0 + (lo << g.nb), (x1 - cx + 1) << g.nb,
+                                            (hi - lo + 1) << g.nb, img_[i].roi.x, img_[i].roi.y, img_[i].roi.w, img_[i].roi.h);
+                if (t >= 0) tiles_of_image_[i].push_back(t);
+                cx = x1 + 1;
+            }
+        }
+        eng_.commit_tiles(st);
         valid_counts_.clear();
         planned_ = true;
     }
@@ -677,7 +763,7 @@ void Composer::run(const isb_image* imgs, const isb_gainmap* gains, const isb_ma
     dyn_.begin();
     std::vector<size_t> src_off(n, 0), gain_off(n, 0), sraw_off(n, 0), sdil_off(n, 0);
     for (int i = 0; i < n; ++i) {
-        if (tile_of_image_[i] < 0) continue;
+        if (tiles_of_image_[i].empty()) continue;
         const isb_image& im = imgs[i];
         if (!im.data) throw Error(ISB_ERR_NULL_PTR, "image data is null");
         ISB_ASSERT(im.width == img_[i].src_w && im.height == img_[i].src_h && im.pitch >= (size_t)im.width * 3);
@@ -700,8 +786,8 @@ void Composer::run(const isb_image* imgs, const isb_gainmap* gains, const isb_ma
     for (int i = 0; i < n; ++i) {
         ImageDev& I = idev[i];
         I = ImageDev{};
-        if (tile_of_image_[i] < 0) continue;
-        const ImagePlan& P = img_[i];
+        if (tiles_of_image_[i].empty()) continue;
+        ImagePlan& P = img_[i];
         const isb_image& im = imgs[i];
         I.sw = P.src_w; I.sh = P.src_h; I.roi_w = P.roi.w; I.roi_h = P.roi.h;
         std::memcpy(I.kr, P.proj.k_rinv, sizeof(I.kr));
@@ -719,10 +805,14 @@ void Composer::run(const isb_image* imgs, const isb_gainmap* gains, const isb_ma
         if (gains && gains[i].data) {
             const isb_gainmap& g = gains[i];
             ISB_CUDA(cudaMemcpyAsync(db + gain_off[i], g.data, (size_t)g.width * g.height * sizeof(float), cudaMemcpyDefault, st));
-            build_linear_f32_table(g.width, P.roi.w, true, gx);
-            build_linear_f32_table(g.height, P.roi.h, false, gy);
-            ISB_CUDA(cudaMemcpyAsync(tb + P.gx_off, gx.data(), gx.size() * sizeof(LinCoefDev), cudaMemcpyHostToDevice, st));
-            ISB_CUDA(cudaMemcpyAsync(tb + P.gy_off, gy.data(), gy.size() * sizeof(LinCoefDev), cudaMemcpyHostToDevice, st));
+            if (P.gain_w != g.width || P.gain_h != g.height) {  // coefficient tables depend on the sizes only
+                build_linear_f32_table(g.width, P.roi.w, true, gx);
+                build_linear_f32_table(g.height, P.roi.h, false, gy);
+                ISB_CUDA(cudaMemcpyAsync(tb + P.gx_off, gx.data(), gx.size() * sizeof(LinCoefDev), cudaMemcpyHostToDevice, st));
+                ISB_CUDA(cudaMemcpyAsync(tb + P.gy_off, gy.data(), gy.size() * sizeof(LinCoefDev), cudaMemcpyHostToDevice, st));
+                P.gain_w = g.width;
+                P.gain_h = g.height;
+            }
             I.gain = reinterpret_cast<const float*>(db + gain_off[i]);
             I.gw = g.width; I.gh = g.height;
             I.gx = reinterpret_cast<const LinCoefDev*>(tb + P.gx_off);
@@ -731,10 +821,14 @@ void Composer::run(const isb_image* imgs, const isb_gainmap* gains, const isb_ma
         if (seams && seams[i].data) {
             const isb_mask& m = seams[i];
             copy2d(db + sraw_off[i], m.width, m.data, m.pitch, m.width, m.height, st);
-            build_linear_exact_table(m.width, P.roi.w, mx);
-            build_linear_exact_table(m.height, P.roi.h, my);
-            ISB_CUDA(cudaMemcpyAsync(tb + P.mx_off, mx.data(), mx.size() * 4, cudaMemcpyHostToDevice, st));
-            ISB_CUDA(cudaMemcpyAsync(tb + P.my_off, my.data(), my.size() * 4, cudaMemcpyHostToDevice, st));
+            if (P.seam_w != m.width || P.seam_h != m.height) {
+                build_linear_exact_table(m.width, P.roi.w, mx);
+                build_linear_exact_table(m.height, P.roi.h, my);
+                ISB_CUDA(cudaMemcpyAsync(tb + P.mx_off, mx.data(), mx.size() * 4, cudaMemcpyHostToDevice, st));
+                ISB_CUDA(cudaMemcpyAsync(tb + P.my_off, my.data(), my.size() * 4, cudaMemcpyHostToDevice, st));
+                P.seam_w = m.width;
+                P.seam_h = m.height;
+            }
             I.seam = reinterpret_cast<const uint8_t*>(db + sdil_off[i]);
             I.mw = m.width; I.mh = m.height;
             I.mx = reinterpret_cast<const uint32_t*>(tb + P.mx_off);
@@ -750,7 +844,7 @@ void Composer::run(const isb_image* imgs, const isb_gainmap* gains, const isb_ma
         if (idev[i].seam)
             launch_dilate3x3(reinterpret_cast<const uint8_t*>(db + sraw_off[i]), idev[i].mw, idev[i].mh, idev[i].mw,
                              reinterpret_cast<uint8_t*>(db + sdil_off[i]), st);
-    launch_warp_tiles(eng_.warp_work_dev(), (int)eng_.warp_work().size(), eng_.tiles_dev(), idp, st);
+    launch_warp_tiles_packed(eng_.warp_work_dev(), (int)eng_.warp_work().size(), eng_.tiles_dev(), idp, st);
     // ---- stage 2: pyramids (kernel 2) ---------------------------------------------------------
     ISB_CUDA(cudaEventRecord(ev_[2], st));
     eng_.build_pyramids(0, (int)eng_.tiles().size(), st);
@@ -801,7 +895,7 @@ void Composer::run(const isb_image* imgs, const isb_gainmap* gains, const isb_ma
     // host-visible results (or host-owned inputs) => the call is synchronous; all-device calls stay stream-ordered
     bool any_host = (out->data && !d8) || (out->mask && !dm) || (out->data16 && !d16);
     for (int i = 0; i < n && !any_host; ++i)
-        if (tile_of_image_[i] >= 0 && mem_kind(imgs[i].data) == MemKind::Host) any_host = true;
+        if (!tiles_of_image_[i].empty() && mem_kind(imgs[i].data) == MemKind::Host) any_host = true;
     if (any_host) ISB_CUDA(cudaStreamSynchronize(st));
 }
 

@@ -82,6 +82,7 @@ struct ImagePlan {
     std::vector<Float2> col, row;
     // offsets into the composer's table arena
     size_t col_off = 0, row_off = 0, gx_off = 0, gy_off = 0, mx_off = 0, my_off = 0;
+    int gain_w = -1, gain_h = -1, seam_w = -1, seam_h = -1;  // sizes the cached coefficient tables were built for
 };
 
 // The pyramid engine: owns the per-tile pyramids and the destination pyramid, runs kernels 2 and 3.
@@ -89,10 +90,15 @@ class PyramidEngine {
 public:
     // Start a blend over the sub-panorama rows [sub_y0, sub_y0 + sub_h) of the padded ROI; rows
     // [own_y0, own_y1) (padded coords) are the ones written to the output.
-    void reset(const BlendGeometry& g, int sub_y0, int sub_h, int own_y0, int own_y1);
+    void reset(const BlendGeometry& g, int sub_y0, int sub_h, int own_y0, int own_y1, bool packed);
     // Add the tile feed() would use for an image at `tl` of size (w x h); clipped to the sub-panorama.
     // Returns the tile index or -1 when the tile does not touch the sub-panorama.
     int add_tile(int img_index, int w, int h, int tlx, int tly);
+    // Same for an explicit rectangle (padded-ROI coordinates, on the 2^nb grid) of the image whose warped ROI
+    // has its top-left at (tlx, tly) in panorama coordinates.
+    int add_rect(int img_index, int X0, int Y0, int W, int H, int tlx, int tly, int roi_w, int roi_h);
+    // pyrDown l -> l+1 has an even output width, so the register-rolling kernel applies
+    bool fast_down(int l) const { return l + 1 < g_.nb; }
     // Allocate pyramid storage for tiles [first, end) (device pointers filled in), upload descriptors.
     void commit_tiles(cudaStream_t st);
     // kernel 2 for tiles [first, end): all levels
@@ -115,7 +121,6 @@ private:
     int sub_y0_ = 0, sub_h_ = 0, own_y0_ = 0, own_y1_ = 0;
     std::vector<TileDev> tiles_;
     int committed_ = 0;           // tiles [0, committed_) have storage
-    std::vector<size_t> tile_off_;  // arena offset of each tile's storage
     Arena arena_;                 // fused path: one block for all tiles
     std::vector<DevBuf*> extra_;  // classic path: one allocation per late-added tile
     DevBuf tiles_dev_, warp_work_dev_, down_work_dev_, cells_dev_, dst_buf_;
@@ -124,7 +129,7 @@ private:
     std::vector<size_t> down_off_;
     PinBuf pin_;
     DstDev dst_{};
-    bool frozen_arena_ = false;
+    bool packed_ = false;
 public:
     ~PyramidEngine();
 };
@@ -198,7 +203,7 @@ private:
     std::vector<isb_camera> cams_;
     std::vector<int> src_sizes_;
     std::vector<ImagePlan> img_;
-    std::vector<int> tile_of_image_;
+    std::vector<std::vector<int>> tiles_of_image_;
     PyramidEngine eng_;
     Rect dst_roi_;
     Arena tables_;              // trig tables (static per plan)

@@ -37,6 +37,23 @@ void launch_pyrdown_tiles(const WorkItem* work, int n_work, const TileDev* tiles
 // accumulate (image order) + normalise + collapse one level of the destination; level 0 writes the output
 void launch_blend_level(const DstDev& dst, const TileDev* tiles, int level, const OutDev& out, cudaStream_t st);
 
+// ---- fast path of the fused composer (kernels_fast.cu): byte-packed level 0 ------------------------
+// occupancy of the valid mask per macro cell (2^nb x 2^nb px, tile-aligned) of every listed tile -> occ (bytes)
+struct OccTile { int img; int left, top; int w, h; long long occ_off; };
+void launch_occupancy(const OccTile* tiles_dev, int n_tiles, int max_w, int max_h, const ImageDev* imgs, int nb,
+                      uint8_t* occ, cudaStream_t st);
+// fused warp -> packed level 0
+void launch_warp_tiles_packed(const WorkItem* work, int n_work, const TileDev* tiles, const ImageDev* imgs, cudaStream_t st);
+// register-rolling separable pyrDown, 2 outputs per thread: packed L0 -> L1 (level == 0) or planar l -> l+1
+void launch_pyrdown_fast(const WorkItem* work, int n_work, const TileDev* tiles, int level, bool packed0, cudaStream_t st);
+// 2x2-quad accumulate + normalise + collapse for level < nb
+void launch_blend_quad(const DstDev& dst, const TileDev* tiles, int level, const OutDev& out, cudaStream_t st);
+void count_launch();
+
+constexpr int kFastDownCols = 64;   // output columns per warp (2 per lane)
+constexpr int kFastDownRows = 16;   // output rows per warp
+constexpr int kFastDownWarps = 8;   // warps per CTA, stacked in y  -> CTA block = 64 x 128 outputs
+
 // geometry of the CTA blocks the planner must use when it builds work lists
 constexpr int kWarpBlockW = 64, kWarpBlockH = 32;
 constexpr int kDownBlockW = 32, kDownBlockH = 8;  // in OUTPUT (level l+1) pixels
