@@ -20,14 +20,22 @@ __device__ __forceinline__ int sat_u8(int v) { return min(max(v, 0), 255); }
 // static_cast<short>(float): cvttss2si then the low 16 bits
 __device__ __forceinline__ int trunc_s16(float v) { return (int)(short)__float2int_rz(v); }
 
-__device__ __forceinline__ int reflect(int p, int n)
-{  // cv::BORDER_REFLECT  fedcba|abcdefgh|hgfedcb, any distance
-    if ((unsigned)p < (unsigned)n) return p;
+// cv::BORDER_REFLECT  fedcba|abcdefgh|hgfedcb.  One reflection covers -n <= p < 2n; farther indices (sentinel
+// coordinates, saturated shorts) take the out-of-line modulo path so the hot path carries no integer division.
+static __device__ __noinline__ int reflect_far(int p, int n)
+{
     if (n == 1) return 0;
     if (p < 0) p = -p - 1;
     const int m = 2 * n;
     p %= m;
     return p < n ? p : m - 1 - p;
+}
+__device__ __forceinline__ int reflect(int p, int n)
+{
+    if ((unsigned)p < (unsigned)n) return p;
+    const int q = p < 0 ? -p - 1 : 2 * n - 1 - p;
+    if ((unsigned)q < (unsigned)n) return q;
+    return reflect_far(p, n);
 }
 __device__ __forceinline__ int reflect101(int p, int n)
 {  // cv::BORDER_REFLECT_101 for |overshoot| < n (pyramid taps overshoot by <= 2)
@@ -147,35 +155,72 @@ __device__ __forceinline__ float wdown_v(float r0, float r1, float r2, float r3,
     return __fmul_rn(v, 1.f / 256.f);
 }
 
-// one pixel of cv::pyrUp(coarse)(to exactly 2x) at fine position (fx, fy): edge rule s[-1]:=s[1], s[n]:=s[n-1]
-__device__ __forceinline__ int pyrup_at(const int16_t* __restrict__ c, int pitch, int wc, int hc, int fx, int fy)
-{
-    const int cx = fx >> 1, cy = fy >> 1;
-    const int xm = cx == 0 ? (wc > 1 ? 1 : 0) : cx - 1, xp = cx == wc - 1 ? cx : cx + 1;
-    const int ym = cy == 0 ? (hc > 1 ? 1 : 0) : cy - 1, yp = cy == hc - 1 ? cy : cy + 1;
-    const int wx0 = (fx & 1) ? 0 : 1, wx1 = (fx & 1) ? 4 : 6, wx2 = (fx & 1) ? 4 : 1;
-    const int wy0 = (fy & 1) ? 0 : 1, wy1 = (fy & 1) ? 4 : 6, wy2 = (fy & 1) ? 4 : 1;
-    const int16_t* r0 = c + (long long)ym * pitch;
-    const int16_t* r1 = c + (long long)cy * pitch;
-    const int16_t* r2 = c + (long long)yp * pitch;
-    const int h0 = wx0 * r0[xm] + wx1 * r0[cx] + wx2 * r0[xp];
-    const int h1 = wx0 * r1[xm] + wx1 * r1[cx] + wx2 * r1[xp];
-    const int h2 = wx0 * r2[xm] + wx1 * r2[cx] + wx2 * r2[xp];
-    return sat_s16((wy0 * h0 + wy1 * h1 + wy2 * h2 + 32) >> 6);
-}
-
-
-
-// level-l sample of a tile's Gaussian / weight pyramid, whichever storage level 0 uses
+// level-l sample of a tile's Gaussian / weight pyramid, whichever storage the tile uses
 __device__ __forceinline__ int tile_g(const TileDev& T, int l, int p, int x, int y)
 {
-    if (l == 0 && T.packed) return (int)((T.P0[(long long)y * T.ppitch + x] >> (8 * p)) & 0xffu);
+    if (T.packed) return (int)((T.P[l][y * T.ppitch[l] + x] >> (8 * p)) & 0xffu);
     return T.G[l][p * T.gplane[l] + (long long)y * T.gpitch[l] + x];
 }
 __device__ __forceinline__ float tile_w(const TileDev& T, int l, int x, int y)
 {
-    if (l == 0 && T.packed) return __fmul_rn((float)(T.P0[(long long)y * T.ppitch + x] >> 24), (float)(1. / 255.));
+    if (l == 0 && T.packed) return __fmul_rn((float)(T.P[0][y * T.ppitch[0] + x] >> 24), (float)(1. / 255.));
     return T.W[l][(long long)y * T.wpitch[l] + x];
+}
+
+// collapsed destination level: 16S x4 interleaved
+__device__ __forceinline__ void c_unpack(uint2 v, int& b, int& g, int& r)
+{
+    b = (short)(v.x & 0xffffu);
+    g = (short)(v.x >> 16);
+    r = (short)(v.y & 0xffffu);
+}
+__device__ __forceinline__ uint2 c_pack(int b, int g, int r)
+{
+    return make_uint2(((uint32_t)b & 0xffffu) | ((uint32_t)g << 16), (uint32_t)r & 0xffffu);
+}
+
+// cv::pyrUp (to exactly 2x) of a collapsed level at one fine position; edge rule s[-1] := s[1], s[n] := s[n-1]
+__device__ __forceinline__ void pyrup_c_at(const uint2* __restrict__ c, int pitch, int wc, int hc, int fx, int fy, int out[3])
+{
+    const int cx = fx >> 1, cy = fy >> 1;
+    const int xi[3] = {cx == 0 ? (wc > 1 ? 1 : 0) : cx - 1, cx, cx == wc - 1 ? cx : cx + 1};
+    const int yi[3] = {cy == 0 ? (hc > 1 ? 1 : 0) : cy - 1, cy, cy == hc - 1 ? cy : cy + 1};
+    const int wx[3] = {(fx & 1) ? 0 : 1, (fx & 1) ? 4 : 6, (fx & 1) ? 4 : 1};
+    const int wy[3] = {(fy & 1) ? 0 : 1, (fy & 1) ? 4 : 6, (fy & 1) ? 4 : 1};
+    int acc[3] = {0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        int h[3] = {0, 0, 0};
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            int b, g, r;
+            c_unpack(c[yi[j] * pitch + xi[i]], b, g, r);
+            h[0] += wx[i] * b; h[1] += wx[i] * g; h[2] += wx[i] * r;
+        }
+        acc[0] += wy[j] * h[0]; acc[1] += wy[j] * h[1]; acc[2] += wy[j] * h[2];
+    }
+#pragma unroll
+    for (int p = 0; p < 3; ++p) out[p] = sat_s16((acc[p] + 32) >> 6);
+}
+
+// the same for one channel of a tile's (l+1) Gaussian level
+__device__ __forceinline__ int pyrup_tile_at(const TileDev& T, int lc, int p, int fx, int fy)
+{
+    const int wc = T.w >> lc, hc = T.h >> lc;
+    const int cx = fx >> 1, cy = fy >> 1;
+    const int xi[3] = {cx == 0 ? (wc > 1 ? 1 : 0) : cx - 1, cx, cx == wc - 1 ? cx : cx + 1};
+    const int yi[3] = {cy == 0 ? (hc > 1 ? 1 : 0) : cy - 1, cy, cy == hc - 1 ? cy : cy + 1};
+    const int wx[3] = {(fx & 1) ? 0 : 1, (fx & 1) ? 4 : 6, (fx & 1) ? 4 : 1};
+    const int wy[3] = {(fy & 1) ? 0 : 1, (fy & 1) ? 4 : 6, (fy & 1) ? 4 : 1};
+    int acc = 0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        int h = 0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) h += wx[i] * tile_g(T, lc, p, xi[i], yi[j]);
+        acc += wy[j] * h;
+    }
+    return sat_s16((acc + 32) >> 6);
 }
 
 }  // namespace isb

@@ -15,6 +15,7 @@ struct LinCoefDev { int ofs; float frac; };
 struct ImageDev {
     const uint8_t* src;   // 8UC3 interleaved (or 8UC1 for mask warps)
     long long spitch;     // bytes
+    unsigned sbytes;      // spitch * sh when the vectorised sampler may be used (8-B aligned base, < 4 GB), else 0
     int sw, sh;           // source size
     int roi_w, roi_h;     // warped size (warpRoi)
     float kr[9];          // k_rinv = K * R^T
@@ -37,11 +38,13 @@ struct TileDev {
     int img;                 // index into ImageDev[] (fused path) or -1 (classic feed)
     int left, top;           // ROI top-left relative to the tile origin (copyMakeBorder's left/top)
     int roi_w, roi_h;        // warped image size (tile px outside are REFLECT padding, weight 0)
-    // Level 0 of the fused path is byte-packed: one uint32 per pixel = b | g<<8 | r<<16 | m<<24, where (b,g,r) is the
-    // gain-compensated 8-bit warp result and m the 8-bit blend mask (weight = m * (1/255), exactly as feed() forms it).
-    // It replaces G[0]/W[0] (10 B/px -> 4 B/px) whenever `packed` is set; the classic feed() path keeps 16S + f32.
-    uint32_t* P0;
-    int ppitch;              // elements
+    // Fused path (`packed` != 0): the warped image is 8-bit, so every Gaussian level stays in [0,255] and is stored
+    // byte-packed, one uint32 per pixel = b | g<<8 | r<<16 (| m<<24 at level 0, m = the 8-bit blend mask, whose
+    // weight is m * (1/255) exactly as feed() forms it).  Level 0 therefore costs 4 B/px instead of 10 B/px and one
+    // 32-bit load fetches all channels.  Weights of levels >= 1 are f32 planes (W).  The classic feed() path
+    // (arbitrary 16S input) keeps planar 16S (G) + f32 (W) at every level.
+    uint32_t* P[kMaxLevels];
+    int ppitch[kMaxLevels];  // elements
     int packed;
     int16_t* G[kMaxLevels];  // plane p at G[l] + p * gplane[l]
     float* W[kMaxLevels];
@@ -58,9 +61,8 @@ struct DstDev {
     int nb;
     int pw, ph;                // padded level-0 size
     int fw, fh;                // final (unpadded) size
-    int16_t* C[kMaxLevels];    // collapsed Laplacian levels 1..nb, planar x3
-    int cpitch[kMaxLevels];
-    long long cplane[kMaxLevels];
+    uint2* C[kMaxLevels];      // collapsed Laplacian levels 1..nb: 16S x4 interleaved (b, g, r, 0) = 8 B per pixel
+    int cpitch[kMaxLevels];    // elements (pixels)
     int cells_x, cells_y;      // macro cells of 2^nb x 2^nb level-0 px
     const int* cell_start;     // CSR: tiles covering each macro cell, ascending feed order
     const int* cell_tiles;

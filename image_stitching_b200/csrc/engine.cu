@@ -158,20 +158,24 @@ void PyramidEngine::commit_tiles(cudaStream_t st)
     Arena local;
     Arena& ar = (first == 0) ? arena_ : local;
     ar.begin();
-    std::vector<size_t> goff((size_t)(end - first) * (nb + 1)), woff(goff.size()), poff(end - first, 0);
+    const size_t nl = (size_t)nb + 1;
+    std::vector<size_t> goff((size_t)(end - first) * nl), woff(goff.size());
     for (int t = first; t < end; ++t) {
         TileDev& T = tiles_[t];
-        if (T.packed) {
-            T.ppitch = round_up(T.w, 4);
-            poff[t - first] = ar.take((size_t)T.ppitch * T.h * sizeof(uint32_t));
-        }
-        for (int l = T.packed ? 1 : 0; l <= nb; ++l) {
+        for (int l = 0; l <= nb; ++l) {
             const int wl = T.w >> l, hl = T.h >> l;
-            T.gpitch[l] = round_up(wl, 8);
+            const size_t k = (size_t)(t - first) * nl + l;
             T.wpitch[l] = round_up(wl, 4);
-            T.gplane[l] = (long long)T.gpitch[l] * hl;
-            goff[(size_t)(t - first) * (nb + 1) + l] = ar.take((size_t)T.gplane[l] * 3 * sizeof(int16_t));
-            woff[(size_t)(t - first) * (nb + 1) + l] = ar.take((size_t)T.wpitch[l] * hl * sizeof(float));
+            if (T.packed) {
+                T.ppitch[l] = round_up(wl, 4);
+                goff[k] = ar.take((size_t)T.ppitch[l] * hl * sizeof(uint32_t));
+                woff[k] = l == 0 ? 0 : ar.take((size_t)T.wpitch[l] * hl * sizeof(float));  // level-0 weight = mask byte
+            } else {
+                T.gpitch[l] = round_up(wl, 8);
+                T.gplane[l] = (long long)T.gpitch[l] * hl;
+                goff[k] = ar.take((size_t)T.gplane[l] * 3 * sizeof(int16_t));
+                woff[k] = ar.take((size_t)T.wpitch[l] * hl * sizeof(float));
+            }
         }
     }
     char* base;
@@ -183,10 +187,11 @@ void PyramidEngine::commit_tiles(cudaStream_t st)
     }
     for (int t = first; t < end; ++t) {
         TileDev& T = tiles_[t];
-        if (T.packed) T.P0 = reinterpret_cast<uint32_t*>(base + poff[t - first]);
-        for (int l = T.packed ? 1 : 0; l <= nb; ++l) {
-            T.G[l] = reinterpret_cast<int16_t*>(base + goff[(size_t)(t - first) * (nb + 1) + l]);
-            T.W[l] = reinterpret_cast<float*>(base + woff[(size_t)(t - first) * (nb + 1) + l]);
+        for (int l = 0; l <= nb; ++l) {
+            const size_t k = (size_t)(t - first) * nl + l;
+            if (T.packed) T.P[l] = reinterpret_cast<uint32_t*>(base + goff[k]);
+            else T.G[l] = reinterpret_cast<int16_t*>(base + goff[k]);
+            T.W[l] = (T.packed && l == 0) ? nullptr : reinterpret_cast<float*>(base + woff[k]);
         }
     }
     // work lists for the new tiles
@@ -200,7 +205,7 @@ void PyramidEngine::commit_tiles(cudaStream_t st)
             const int ow = T.w >> (l + 1), oh = T.h >> (l + 1);
             // levels with an even output width run the register-rolling kernel (64 x 128 outputs per CTA)
             const int bw = fast_down(l) ? kFastDownCols : kDownBlockW;
-            const int bh = fast_down(l) ? kFastDownRows * kFastDownWarps : kDownBlockH;
+            const int bh = fast_down(l) ? fast_rows(l) * kFastDownWarps : kDownBlockH;
             for (int by = 0; by < (oh + bh - 1) / bh; ++by)
                 for (int bx = 0; bx < (ow + bw - 1) / bw; ++bx) down_work_[l].push_back(WorkItem{t, bx, by, 0});
         }
@@ -237,7 +242,7 @@ void PyramidEngine::build_pyramids(int first, int end, cudaStream_t st)
     const WorkItem* base = down_work_dev_.as<WorkItem>();
     for (int l = 0; l < g_.nb; ++l) {
         const int n = (int)(down_off_[l + 1] - down_off_[l]);
-        if (fast_down(l)) launch_pyrdown_fast(base + down_off_[l], n, tiles_dev(), l, packed_ && l == 0, st);
+        if (fast_down(l)) launch_pyrdown_fast(base + down_off_[l], n, tiles_dev(), l, packed_, fast_rows(l), st);
         else launch_pyrdown_tiles(base + down_off_[l], n, tiles_dev(), l, st);
     }
 }
@@ -273,13 +278,12 @@ void PyramidEngine::blend(const OutDev& out, cudaStream_t st)
         size_t cbytes = 0;
         std::vector<size_t> coff(nb + 1, 0);
         for (int l = 1; l <= nb; ++l) {
-            dst_.cpitch[l] = round_up(dst_.pw >> l, 8);
-            dst_.cplane[l] = (long long)dst_.cpitch[l] * (dst_.ph >> l);
+            dst_.cpitch[l] = round_up(dst_.pw >> l, 2);
             coff[l] = cbytes;
-            cbytes += ((size_t)dst_.cplane[l] * 3 * sizeof(int16_t) + 255) & ~size_t(255);
+            cbytes += ((size_t)dst_.cpitch[l] * (dst_.ph >> l) * sizeof(uint2) + 255) & ~size_t(255);
         }
         char* cb = static_cast<char*>(dst_buf_.ensure(std::max<size_t>(cbytes, 256)));
-        for (int l = 1; l <= nb; ++l) dst_.C[l] = reinterpret_cast<int16_t*>(cb + coff[l]);
+        for (int l = 1; l <= nb; ++l) dst_.C[l] = reinterpret_cast<uint2*>(cb + coff[l]);
         int* cd = static_cast<int*>(cells_dev_.ensure((start.size() + list.size()) * sizeof(int)));
         ISB_CUDA(cudaMemcpyAsync(cd, start.data(), start.size() * sizeof(int), cudaMemcpyHostToDevice, st));
         ISB_CUDA(cudaMemcpyAsync(cd + start.size(), list.data(), list.size() * sizeof(int), cudaMemcpyHostToDevice, st));
@@ -610,7 +614,9 @@ void Composer::plan(const isb_camera* cams, const int* sizes_wh, int n, int* cor
             P.proj.set(cfg_.warp_kind, cfg_.warped_image_scale, K, cams[i].R);
             P.roi = P.proj.warp_roi(P.src_w, P.src_h);
         };
-        for (int i = 0; i < n; ++i) ISB_ASSERT(sizes_wh[2 * i] > 0 && sizes_wh[2 * i + 1] > 0);
+        // cv::remap itself requires source sizes below SHRT_MAX; the fused sampler relies on it too
+        for (int i = 0; i < n; ++i)
+            ISB_ASSERT(sizes_wh[2 * i] > 0 && sizes_wh[2 * i + 1] > 0 && sizes_wh[2 * i] < 32767 && sizes_wh[2 * i + 1] < 32767);
         const int nthr = std::max(1, std::min<int>(n, std::min(16u, std::thread::hardware_concurrency())));
         if (nthr <= 1) {
             for (int i = 0; i < n; ++i) work(i);
@@ -801,6 +807,10 @@ void Composer::run(const isb_image* imgs, const isb_gainmap* gains, const isb_ma
             copy2d(db + src_off[i], rb, im.data, im.pitch, rb, im.height, st);
             I.src = reinterpret_cast<const uint8_t*>(db + src_off[i]);
             I.spitch = (long long)rb;
+        }
+        {   // the vectorised sampler reads aligned 16-byte windows: needs an 8-B aligned base and 32-bit offsets
+            const unsigned long long extent = (unsigned long long)I.spitch * (I.sh - 1) + (unsigned long long)I.sw * 3;
+            I.sbytes = ((reinterpret_cast<uintptr_t>(I.src) & 7) == 0 && extent < 0xFFFFFF00ull) ? (unsigned)extent : 0u;
         }
         if (gains && gains[i].data) {
             const isb_gainmap& g = gains[i];

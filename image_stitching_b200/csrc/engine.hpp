@@ -99,6 +99,8 @@ public:
     int add_rect(int img_index, int X0, int Y0, int W, int H, int tlx, int tly, int roi_w, int roi_h);
     // pyrDown l -> l+1 has an even output width, so the register-rolling kernel applies
     bool fast_down(int l) const { return l + 1 < g_.nb; }
+    static int fast_rows(int l) { return l == 0 ? kFastDownRowsDefault : kFastDownRowsCoarse; }
+    static constexpr int kFastDownRowsDefault = 16, kFastDownRowsCoarse = 4;  // == kernels.cuh kFastDownRows / ...Small
     // Allocate pyramid storage for tiles [first, end) (device pointers filled in), upload descriptors.
     void commit_tiles(cudaStream_t st);
     // kernel 2 for tiles [first, end): all levels

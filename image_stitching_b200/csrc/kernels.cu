@@ -297,6 +297,7 @@ __global__ void __launch_bounds__(256) pyrdown_tiles_kernel(const WorkItem* __re
     }
     // 16S planes: integer 5x5 [1 4 6 4 1], (sum + 128) >> 8
     const int gpo = T.gpitch[l + 1];
+    int outg[3];
 #pragma unroll
     for (int p = 0; p < 3; ++p) {
         int acc = 0;
@@ -306,7 +307,12 @@ __global__ void __launch_bounds__(256) pyrdown_tiles_kernel(const WorkItem* __re
                           4 * (tile_g(T, l, p, xs[1], ys[j]) + tile_g(T, l, p, xs[3], ys[j])) + 6 * tile_g(T, l, p, xs[2], ys[j]);
             acc += (j == 0 || j == 4) ? h : ((j == 2) ? 6 * h : 4 * h);
         }
-        T.G[l + 1][p * T.gplane[l + 1] + (long long)oy * gpo + ox] = (int16_t)((acc + 128) >> 8);
+        outg[p] = (acc + 128) >> 8;
+    }
+    if (T.packed) T.P[l + 1][oy * T.ppitch[l + 1] + ox] = (uint32_t)outg[0] | ((uint32_t)outg[1] << 8) | ((uint32_t)outg[2] << 16);
+    else {
+#pragma unroll
+        for (int p = 0; p < 3; ++p) T.G[l + 1][p * T.gplane[l + 1] + (long long)oy * gpo + ox] = (int16_t)outg[p];
     }
     // weight plane
     int width0 = (wl - 3) / 2 + 1;
@@ -355,11 +361,9 @@ __global__ void __launch_bounds__(256) blend_level_kernel(DstDev D, const TileDe
         if (w != 0.f) {
             int v0 = tile_g(T, l, 0, lx, ly), v1 = tile_g(T, l, 1, lx, ly), v2 = tile_g(T, l, 2, lx, ly);
             if (l < D.nb) {
-                const int wc = T.w >> (l + 1), hc = T.h >> (l + 1), cp = T.gpitch[l + 1];
-                const int16_t* c = T.G[l + 1];
-                v0 = sat_s16(v0 - pyrup_at(c, cp, wc, hc, lx, ly));
-                v1 = sat_s16(v1 - pyrup_at(c + T.gplane[l + 1], cp, wc, hc, lx, ly));
-                v2 = sat_s16(v2 - pyrup_at(c + 2 * T.gplane[l + 1], cp, wc, hc, lx, ly));
+                v0 = sat_s16(v0 - pyrup_tile_at(T, l + 1, 0, lx, ly));
+                v1 = sat_s16(v1 - pyrup_tile_at(T, l + 1, 1, lx, ly));
+                v2 = sat_s16(v2 - pyrup_tile_at(T, l + 1, 2, lx, ly));
             }
             acc0 += trunc_s16(__fmul_rn((float)v0, w));
             acc1 += trunc_s16(__fmul_rn((float)v1, w));
@@ -372,17 +376,14 @@ __global__ void __launch_bounds__(256) blend_level_kernel(DstDev D, const TileDe
     int r1 = trunc_s16(__fdiv_rn((float)(short)acc1, den));
     int r2 = trunc_s16(__fdiv_rn((float)(short)acc2, den));
     if (l < D.nb) {
-        const int wc = D.pw >> (l + 1), hc = D.ph >> (l + 1), cp = D.cpitch[l + 1];
-        const int16_t* c = D.C[l + 1];
-        r0 = sat_s16(pyrup_at(c, cp, wc, hc, x, y) + r0);
-        r1 = sat_s16(pyrup_at(c + D.cplane[l + 1], cp, wc, hc, x, y) + r1);
-        r2 = sat_s16(pyrup_at(c + 2 * D.cplane[l + 1], cp, wc, hc, x, y) + r2);
+        int up[3];
+        pyrup_c_at(D.C[l + 1], D.cpitch[l + 1], D.pw >> (l + 1), D.ph >> (l + 1), x, y, up);
+        r0 = sat_s16(up[0] + r0);
+        r1 = sat_s16(up[1] + r1);
+        r2 = sat_s16(up[2] + r2);
     }
     if (l > 0) {
-        int16_t* c = D.C[l] + (long long)y * D.cpitch[l] + x;
-        c[0] = (int16_t)r0;
-        c[D.cplane[l]] = (int16_t)r1;
-        c[2 * D.cplane[l]] = (int16_t)r2;
+        D.C[l][y * D.cpitch[l] + x] = c_pack(r0, r1, r2);
         return;
     }
     if (x >= D.fw || y >= D.fh) return;

@@ -44,14 +44,16 @@ void launch_occupancy(const OccTile* tiles_dev, int n_tiles, int max_w, int max_
                       uint8_t* occ, cudaStream_t st);
 // fused warp -> packed level 0
 void launch_warp_tiles_packed(const WorkItem* work, int n_work, const TileDev* tiles, const ImageDev* imgs, cudaStream_t st);
-// register-rolling separable pyrDown, 2 outputs per thread: packed L0 -> L1 (level == 0) or planar l -> l+1
-void launch_pyrdown_fast(const WorkItem* work, int n_work, const TileDev* tiles, int level, bool packed0, cudaStream_t st);
+// register-rolling separable pyrDown, 2 outputs per thread (packed or planar storage)
+void launch_pyrdown_fast(const WorkItem* work, int n_work, const TileDev* tiles, int level, bool packed, int rows_per_warp,
+                         cudaStream_t st);
 // 2x2-quad accumulate + normalise + collapse for level < nb
 void launch_blend_quad(const DstDev& dst, const TileDev* tiles, int level, const OutDev& out, cudaStream_t st);
 void count_launch();
 
 constexpr int kFastDownCols = 64;   // output columns per warp (2 per lane)
-constexpr int kFastDownRows = 16;   // output rows per warp
+constexpr int kFastDownRows = 16;   // output rows per warp (level 0 -> 1)
+constexpr int kFastDownRowsSmall = 4;  // ... at the coarser levels, where parallelism matters more than halo reuse
 constexpr int kFastDownWarps = 8;   // warps per CTA, stacked in y  -> CTA block = 64 x 128 outputs
 
 // geometry of the CTA blocks the planner must use when it builds work lists
