@@ -200,30 +200,15 @@ def run_ours(args, rank, world):
         if world > 1:
             gather_strips(r["strip_rows"])
 
-    all_rows = [None] * world
+    from image_stitching_b200 import strips
+    m_ = 1 << rig.nb  # the rigs' band counts are below the prepare() clamp, so nb is the actual band count
+    padded_h = (ph + m_ - 1) // m_ * m_
+    all_rows = strips.all_strip_rows(padded_h, ph, rig.nb, world)
 
     def gather_strips(rows):
-        # strips -> rank 0 (full-width rows are contiguous slices of the panorama tensors)
-        if all_rows[0] is None:
-            t = torch.tensor(list(rows), device=dev, dtype=torch.int32)
-            lst = [torch.zeros_like(t) for _ in range(world)]
-            dist.all_gather(lst, t)
-            for i, v in enumerate(lst):
-                all_rows[i] = tuple(int(x) for x in v.cpu())
-        if rank == 0:
-            reqs = []
-            for r in range(1, world):
-                y0, y1 = all_rows[r]
-                if y1 > y0:
-                    reqs.append(dist.irecv(d_out[y0:y1], src=r))
-                    reqs.append(dist.irecv(d_mask[y0:y1], src=r))
-            for q in reqs:
-                q.wait()
-        else:
-            y0, y1 = rows
-            if y1 > y0:
-                dist.send(d_out[y0:y1], dst=0)
-                dist.send(d_mask[y0:y1], dst=0)
+        # strips -> rank 0 over NCCL (full-width rows are contiguous slices of the panorama tensors)
+        assert tuple(rows) == tuple(all_rows[rank])
+        strips.gather_strips([d_out, d_mask], all_rows, rank, world)
 
     def barrier():
         if world > 1:

@@ -26,6 +26,8 @@ struct ImageDev {
     const LinCoefDev* gx; // [roi_w]
     const LinCoefDev* gy; // [roi_h]
     const uint8_t* seam;  // dilated low-res seam mask mh x mw, tight pitch (nullptr: all 255)
+    const uint8_t* seam_raw;  // the caller's seam mask (input of the batched 3x3 dilate), pitch seam_raw_pitch
+    int seam_raw_pitch;
     int mw, mh;
     const uint32_t* mx;   // [roi_w] (ofs << 16) | alpha
     const uint32_t* my;   // [roi_h]

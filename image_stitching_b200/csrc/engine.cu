@@ -776,11 +776,12 @@ void Composer::run(const isb_image* imgs, const isb_gainmap* gains, const isb_ma
         if (mem_kind(im.data) != MemKind::Device) src_off[i] = dyn_.take((size_t)im.width * 3 * im.height);
         if (gains && gains[i].data) {
             ISB_ASSERT(gains[i].width > 0 && gains[i].height > 0);
-            gain_off[i] = dyn_.take((size_t)gains[i].width * gains[i].height * sizeof(float));
+            if (mem_kind(gains[i].data) != MemKind::Device)
+                gain_off[i] = dyn_.take((size_t)gains[i].width * gains[i].height * sizeof(float));
         }
         if (seams && seams[i].data) {
             ISB_ASSERT(seams[i].width > 0 && seams[i].height > 0 && seams[i].pitch >= (size_t)seams[i].width);
-            sraw_off[i] = dyn_.take((size_t)seams[i].width * seams[i].height);
+            if (mem_kind(seams[i].data) != MemKind::Device) sraw_off[i] = dyn_.take((size_t)seams[i].width * seams[i].height);
             sdil_off[i] = dyn_.take((size_t)seams[i].width * seams[i].height);
         }
     }
@@ -789,6 +790,7 @@ void Composer::run(const isb_image* imgs, const isb_gainmap* gains, const isb_ma
     std::vector<ImageDev> idev(n);
     std::vector<LinCoef> gx, gy;
     std::vector<uint32_t> mx, my;
+    int max_mw = 0, max_mh = 0;
     for (int i = 0; i < n; ++i) {
         ImageDev& I = idev[i];
         I = ImageDev{};
@@ -814,7 +816,8 @@ void Composer::run(const isb_image* imgs, const isb_gainmap* gains, const isb_ma
         }
         if (gains && gains[i].data) {
             const isb_gainmap& g = gains[i];
-            ISB_CUDA(cudaMemcpyAsync(db + gain_off[i], g.data, (size_t)g.width * g.height * sizeof(float), cudaMemcpyDefault, st));
+            const bool gdev = mem_kind(g.data) == MemKind::Device;  // device-resident gain maps are used in place
+            if (!gdev) ISB_CUDA(cudaMemcpyAsync(db + gain_off[i], g.data, (size_t)g.width * g.height * sizeof(float), cudaMemcpyDefault, st));
             if (P.gain_w != g.width || P.gain_h != g.height) {  // coefficient tables depend on the sizes only
                 build_linear_f32_table(g.width, P.roi.w, true, gx);
                 build_linear_f32_table(g.height, P.roi.h, false, gy);
@@ -823,14 +826,23 @@ void Composer::run(const isb_image* imgs, const isb_gainmap* gains, const isb_ma
                 P.gain_w = g.width;
                 P.gain_h = g.height;
             }
-            I.gain = reinterpret_cast<const float*>(db + gain_off[i]);
+            I.gain = gdev ? g.data : reinterpret_cast<const float*>(db + gain_off[i]);
             I.gw = g.width; I.gh = g.height;
             I.gx = reinterpret_cast<const LinCoefDev*>(tb + P.gx_off);
             I.gy = reinterpret_cast<const LinCoefDev*>(tb + P.gy_off);
         }
         if (seams && seams[i].data) {
             const isb_mask& m = seams[i];
-            copy2d(db + sraw_off[i], m.width, m.data, m.pitch, m.width, m.height, st);
+            if (mem_kind(m.data) == MemKind::Device) {
+                I.seam_raw = m.data;
+                I.seam_raw_pitch = (int)m.pitch;
+            } else {
+                copy2d(db + sraw_off[i], m.width, m.data, m.pitch, m.width, m.height, st);
+                I.seam_raw = reinterpret_cast<const uint8_t*>(db + sraw_off[i]);
+                I.seam_raw_pitch = m.width;
+            }
+            max_mw = std::max(max_mw, m.width);
+            max_mh = std::max(max_mh, m.height);
             if (P.seam_w != m.width || P.seam_h != m.height) {
                 build_linear_exact_table(m.width, P.roi.w, mx);
                 build_linear_exact_table(m.height, P.roi.h, my);
@@ -850,10 +862,7 @@ void Composer::run(const isb_image* imgs, const isb_gainmap* gains, const isb_ma
 
     // ---- stage 1: seam dilate + fused warp (kernel 1) ---------------------------------------
     ISB_CUDA(cudaEventRecord(ev_[1], st));
-    for (int i = 0; i < n; ++i)
-        if (idev[i].seam)
-            launch_dilate3x3(reinterpret_cast<const uint8_t*>(db + sraw_off[i]), idev[i].mw, idev[i].mh, idev[i].mw,
-                             reinterpret_cast<uint8_t*>(db + sdil_off[i]), st);
+    launch_dilate_seams(idp, n, max_mw, max_mh, st);
     launch_warp_tiles_packed(eng_.warp_work_dev(), (int)eng_.warp_work().size(), eng_.tiles_dev(), idp, st);
     // ---- stage 2: pyramids (kernel 2) ---------------------------------------------------------
     ISB_CUDA(cudaEventRecord(ev_[2], st));

@@ -42,6 +42,8 @@ void launch_blend_level(const DstDev& dst, const TileDev* tiles, int level, cons
 struct OccTile { int img; int left, top; int w, h; long long occ_off; };
 void launch_occupancy(const OccTile* tiles_dev, int n_tiles, int max_w, int max_h, const ImageDev* imgs, int nb,
                       uint8_t* occ, cudaStream_t st);
+// cv::dilate(3x3) of every image's seam mask in one launch: imgs[i].seam_raw -> imgs[i].seam
+void launch_dilate_seams(const ImageDev* imgs_dev, int n_img, int max_w, int max_h, cudaStream_t st);
 // fused warp -> packed level 0
 void launch_warp_tiles_packed(const WorkItem* work, int n_work, const TileDev* tiles, const ImageDev* imgs, cudaStream_t st);
 // register-rolling separable pyrDown, 2 outputs per thread (packed or planar storage)
