@@ -22,18 +22,19 @@ def gather_strips(tensors, rows, rank, world, dst=0):
     Returns after the receives have completed on `dst` (stream-ordered on NCCL)."""
     if world == 1:
         return
+    ops = []
     if rank == dst:
-        reqs = []
         for r in range(world):
             y0, y1 = rows[r]
             if r == dst or y1 <= y0:
                 continue
             for t in tensors:
-                reqs.append(dist.irecv(t[y0:y1], src=r))
-        for q in reqs:
-            q.wait()
+                ops.append(dist.P2POp(dist.irecv, t[y0:y1], r))
     else:
         y0, y1 = rows[rank]
         if y1 > y0:
             for t in tensors:
-                dist.send(t[y0:y1], dst=dst)
+                ops.append(dist.P2POp(dist.isend, t[y0:y1], dst))
+    if ops:  # one grouped launch (ncclGroupStart/End): all strips move concurrently over NVLink
+        for q in dist.batch_isend_irecv(ops):
+            q.wait()
