@@ -192,23 +192,36 @@ def run_ours(args, rank, world):
     d_imgs = [torch.from_numpy(im).to(dev) for im in imgs]
     d_gains = [torch.from_numpy(g).to(dev) for g in gains]
     d_seams = [torch.from_numpy(s).to(dev) for s in seams]
-    d_out = torch.zeros((ph, pw, 3), dtype=torch.uint8, device=dev)
-    d_mask = torch.zeros((ph, pw), dtype=torch.uint8, device=dev)
+    from image_stitching_b200 import strips
+    m_ = 1 << rig.nb  # the rigs' band counts are below the prepare() clamp, so nb is the actual band count
+    padded_h = (ph + m_ - 1) // m_ * m_
+    all_rows = strips.all_strip_rows(padded_h, ph, rig.nb, world)
+    use_p2p = world > 1 and args.gather == "p2p"
+    if use_p2p:
+        # fused collapse + gather: rank 0 owns the panorama, the other ranks map it through CUDA IPC and their final
+        # blend kernel stores its rows straight into rank 0's HBM over NVLink (no separate collective, no staging)
+        if rank == 0:
+            d_out, d_mask = isb.DevPtr.alloc((ph, pw, 3)), isb.DevPtr.alloc((ph, pw))
+            handles = [d_out.ipc_handle(), d_mask.ipc_handle()]
+        else:
+            handles = [None, None]
+        dist.broadcast_object_list(handles, src=0)
+        if rank != 0:
+            d_out, d_mask = isb.DevPtr.open_ipc(handles[0], (ph, pw, 3)), isb.DevPtr.open_ipc(handles[1], (ph, pw))
+    else:
+        d_out = torch.zeros((ph, pw, 3), dtype=torch.uint8, device=dev)
+        d_mask = torch.zeros((ph, pw), dtype=torch.uint8, device=dev)
+
+    def gather_strips(rows):
+        # strips -> rank 0 over NCCL (full-width rows are contiguous slices of the panorama tensors)
+        assert tuple(rows) == tuple(all_rows[rank])
+        if not use_p2p:
+            strips.gather_strips([d_out, d_mask], all_rows, rank, world)
 
     def step_device():
         r = comp.run(d_imgs, d_gains, d_seams, out=d_out, out_mask=d_mask)
         if world > 1:
             gather_strips(r["strip_rows"])
-
-    from image_stitching_b200 import strips
-    m_ = 1 << rig.nb  # the rigs' band counts are below the prepare() clamp, so nb is the actual band count
-    padded_h = (ph + m_ - 1) // m_ * m_
-    all_rows = strips.all_strip_rows(padded_h, ph, rig.nb, world)
-
-    def gather_strips(rows):
-        # strips -> rank 0 over NCCL (full-width rows are contiguous slices of the panorama tensors)
-        assert tuple(rows) == tuple(all_rows[rank])
-        strips.gather_strips([d_out, d_mask], all_rows, rank, world)
 
     def barrier():
         if world > 1:
@@ -258,10 +271,17 @@ def run_ours(args, rank, world):
         else:
             r = comp.run([t.numpy() for t in h_imgs], gains, seams, out=d_out, out_mask=d_mask)
             gather_strips(r["strip_rows"])
-            if rank == 0:
-                h_out.copy_(d_out, non_blocking=True)
-                h_mask.copy_(d_mask, non_blocking=True)
+            if use_p2p:
                 torch.cuda.synchronize()
+                dist.barrier()  # every rank's rows have landed in rank 0's panorama
+            if rank == 0:
+                if use_p2p:
+                    d_out.to_numpy(out=h_out.numpy())
+                    d_mask.to_numpy(out=h_mask.numpy())
+                else:
+                    h_out.copy_(d_out, non_blocking=True)
+                    h_mask.copy_(d_mask, non_blocking=True)
+                    torch.cuda.synchronize()
 
     e2e_steps = max(2, min(args.steps, 10))
     ms_e2e = timed(step_e2e, e2e_steps, 2)
@@ -291,12 +311,13 @@ def run_ours(args, rank, world):
             traffic = json.load(open(tp)).get("dram_bytes_per_step")
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s", "frac": achieved / (peak * world),
+                "peak_per_gpu": peak,
                 "traffic": traffic, "peak_source": peak_src,
                 "kernel": "whole compose step: warp_tiles + pyrdown_tiles x nb + blend_level x (nb+1)",
                 "algorithmic_bytes_per_step": bm["B_alg"], "S_px": S, "M_px": M, "Ap_px": Ap,
                 "stages_ms": stage,
-                "stages_frac": {k: (alg[k] / (stage[k] / 1e3) / 1e9 / peak if stage.get(k) else None) for k in alg}}
+                "stages_frac": {k: (alg[k] / (stage[k] / 1e3) / 1e9 / (peak * world) if stage.get(k) else None) for k in alg}}
 
     # ---- CPU baseline (reference CPU path, bounded: one full pass) + full-size parity --------------------
     cpu = None
@@ -326,7 +347,7 @@ def run_ours(args, rank, world):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u8/s16/f32", "data": "synthetic",
             "config": {"workload": workload_name(rig, args), "panorama": [pw, ph], "output_MP": out_mp,
-                       "parallelism": f"strips{world}", "plan_cache": True,
+                       "parallelism": f"strips{world}" + ("" if world == 1 else "+" + args.gather + "-gather"), "plan_cache": True,
                        "l2": "per-step working set (sources + per-image pyramids) >> 126 MB L2; no explicit flush"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps},
@@ -347,6 +368,8 @@ def main():
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--div", type=int, default=1, help="linear down-scale of the rig (dev only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: final kernel stores into rank 0's panorama over NVLink peer memory (p2p) or NCCL send/recv")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", 0))

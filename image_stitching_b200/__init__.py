@@ -112,10 +112,54 @@ def _is_torch(a):
     return type(a).__module__.startswith("torch")
 
 
+class DevPtr:
+    """A raw device pointer (own allocation or a peer buffer opened through CUDA IPC) with an array shape."""
+
+    def __init__(self, ptr, shape, owner=False, ipc=False):
+        self.ptr, self.shape, self._owner, self._ipc = int(ptr), tuple(shape), owner, ipc
+
+    @staticmethod
+    def alloc(shape, itemsize=1):
+        n = int(np.prod(shape)) * itemsize
+        p = C.c_void_p()
+        _chk(lib().isb_device_malloc(C.c_size_t(n), C.byref(p)))
+        return DevPtr(p.value, shape, owner=True)
+
+    def nbytes(self, itemsize=1):
+        return int(np.prod(self.shape)) * itemsize
+
+    def ipc_handle(self):
+        h = (C.c_ubyte * 64)()
+        _chk(lib().isb_ipc_get_handle(C.c_void_p(self.ptr), h))
+        return bytes(h)
+
+    @staticmethod
+    def open_ipc(handle, shape):
+        h = (C.c_ubyte * 64)(*handle)
+        p = C.c_void_p()
+        _chk(lib().isb_ipc_open_handle(h, C.byref(p)))
+        return DevPtr(p.value, shape, ipc=True)
+
+    def to_numpy(self, dtype=np.uint8, out=None):
+        out = np.empty(self.shape, dtype) if out is None else out
+        _chk(lib().isb_memcpy(out.ctypes.data_as(C.c_void_p), C.c_void_p(self.ptr), C.c_size_t(out.nbytes), 1))
+        return out
+
+    def close(self):
+        if self.ptr:
+            if self._ipc:
+                lib().isb_ipc_close_handle(C.c_void_p(self.ptr))
+            elif self._owner:
+                lib().isb_device_free(C.c_void_p(self.ptr))
+            self.ptr = 0
+
+
 def _ptr(a):
     """(address, keepalive) of a numpy array or torch tensor."""
     if a is None:
         return None, None
+    if isinstance(a, DevPtr):
+        return a.ptr, a
     if _is_torch(a):
         a = a if a.is_contiguous() else a.contiguous()
         return a.data_ptr(), a

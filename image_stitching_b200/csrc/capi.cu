@@ -387,6 +387,45 @@ int isb_compose(const isb_image* imgs, const isb_camera* cams, const isb_gainmap
         ISB_CUDA(cudaStreamSynchronize(current_stream()));
     });
 }
+int isb_device_malloc(size_t bytes, void** p)
+{
+    return guarded([&] { NOT_NULL(p); require_device(); ISB_CUDA(cudaMalloc(p, bytes ? bytes : 1)); });
+}
+int isb_device_free(void* p)
+{
+    return guarded([&] { if (p) ISB_CUDA(cudaFree(p)); });
+}
+int isb_ipc_get_handle(const void* p, unsigned char handle[64])
+{
+    return guarded([&] {
+        NOT_NULL(p); NOT_NULL(handle);
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+        cudaIpcMemHandle_t h;
+        ISB_CUDA(cudaIpcGetMemHandle(&h, const_cast<void*>(p)));
+        std::memcpy(handle, &h, 64);
+    });
+}
+int isb_ipc_open_handle(const unsigned char handle[64], void** p)
+{
+    return guarded([&] {
+        NOT_NULL(p); NOT_NULL(handle);
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, handle, 64);
+        ISB_CUDA(cudaIpcOpenMemHandle(p, h, cudaIpcMemLazyEnablePeerAccess));
+    });
+}
+int isb_ipc_close_handle(void* p)
+{
+    return guarded([&] { if (p) ISB_CUDA(cudaIpcCloseMemHandle(p)); });
+}
+int isb_memcpy(void* dst, const void* src, size_t bytes, int synchronize)
+{
+    return guarded([&] {
+        NOT_NULL(dst); NOT_NULL(src);
+        ISB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, current_stream()));
+        if (synchronize) ISB_CUDA(cudaStreamSynchronize(current_stream()));
+    });
+}
 int isb_strip_rows(int padded_h, int final_h, int nb, int idx, int count, int* y0, int* y1)
 {
     return guarded([&] {

@@ -233,6 +233,17 @@ ISB_API int isb_composer_byte_model(isb_composer* c, double* S_px, double* M_px,
 ISB_API int isb_compose(const isb_image* imgs, const isb_camera* cams, const isb_gainmap* gains, const isb_mask* seam_masks,
                         int n, const isb_config* cfg, isb_pano* out);
 
+/* Peer-memory plumbing for the fused "collapse + gather" of the strip-sharded path: rank 0 allocates the panorama
+ * with isb_device_malloc and exports it; the other ranks open the handle and pass the returned pointer as
+ * isb_pano.data / .mask, so that the final blend kernel stores its rows straight into rank 0's HBM over NVLink. */
+ISB_API int isb_device_malloc(size_t bytes, void** dev_ptr);
+ISB_API int isb_device_free(void* dev_ptr);
+ISB_API int isb_ipc_get_handle(const void* dev_ptr, unsigned char handle[64]);
+ISB_API int isb_ipc_open_handle(const unsigned char handle[64], void** dev_ptr);
+ISB_API int isb_ipc_close_handle(void* dev_ptr);
+/* cudaMemcpyAsync(cudaMemcpyDefault) on the library's stream, for moving results out of such buffers */
+ISB_API int isb_memcpy(void* dst, const void* src, size_t bytes, int synchronize);
+
 /* Strip planner (multi-GPU): rows [y0,y1) of the padded panorama owned by strip i of n, boundaries on the 2^nb grid */
 ISB_API int isb_strip_rows(int padded_h, int final_h, int num_bands, int strip_index, int strip_count, int* y0, int* y1);
 
