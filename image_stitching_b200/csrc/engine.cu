@@ -6,9 +6,30 @@
 #include <cstring>
 #include <thread>
 
+#include <cuda.h>
+
 #include "kernels.cuh"
 
 namespace isb {
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (libcuda is not linked)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            p = nullptr;
+        }
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
 
 // ------------------------------------------------------------------------------------------------
 // plumbing
@@ -210,6 +231,35 @@ void PyramidEngine::commit_tiles(cudaStream_t st)
                 for (int bx = 0; bx < (ow + bw - 1) / bw; ++bx) down_work_[l].push_back(WorkItem{t, bx, by, 0});
         }
     }
+    // level 0 -> 1 of the fused path goes through TMA-staged tiles when every tile can hold a full box
+    use_tma_ = false;
+    if (packed_ && first == 0 && nb >= 2 && encode_tiled_fn()) {
+        bool ok = true;
+        for (const TileDev& T : tiles_) ok = ok && T.w >= kTmaBoxW && T.h >= kTmaBoxH;
+        std::vector<CUtensorMap> maps(tiles_.size());
+        for (size_t t = 0; ok && t < tiles_.size(); ++t) {
+            const TileDev& T = tiles_[t];
+            const cuuint64_t dims[2] = {(cuuint64_t)T.w, (cuuint64_t)T.h};
+            const cuuint64_t strides[1] = {(cuuint64_t)T.ppitch[0] * sizeof(uint32_t)};
+            const cuuint32_t box[2] = {(cuuint32_t)kTmaBoxW, (cuuint32_t)kTmaBoxH};
+            const cuuint32_t estr[2] = {1, 1};
+            ok = encode_tiled_fn()(&maps[t], CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, T.P[0], dims, strides, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+        }
+        if (ok) {
+            down_work_[0].clear();
+            for (int t = 0; t < (int)tiles_.size(); ++t) {
+                const int ow = tiles_[t].w >> 1, oh = tiles_[t].h >> 1;
+                for (int by = 0; by < (oh + kTmaOutH - 1) / kTmaOutH; ++by)
+                    for (int bx = 0; bx < (ow + kTmaOutW - 1) / kTmaOutW; ++bx) down_work_[0].push_back(WorkItem{t, bx, by, 0});
+            }
+            void* md = tmaps_dev_.ensure(maps.size() * sizeof(CUtensorMap));
+            ISB_CUDA(cudaMemcpyAsync(md, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, st));
+            ISB_CUDA(cudaStreamSynchronize(st));  // `maps` is a local
+            use_tma_ = true;
+        }
+    }
     // uploads (pageable sources: the runtime stages them before returning, so the vectors may be reused)
     TileDev* td = static_cast<TileDev*>(tiles_dev_.ensure(std::max<size_t>(tiles_.size(), 16) * 2 * sizeof(TileDev)));
     ISB_CUDA(cudaMemcpyAsync(td, tiles_.data(), tiles_.size() * sizeof(TileDev), cudaMemcpyHostToDevice, st));
@@ -242,7 +292,8 @@ void PyramidEngine::build_pyramids(int first, int end, cudaStream_t st)
     const WorkItem* base = down_work_dev_.as<WorkItem>();
     for (int l = 0; l < g_.nb; ++l) {
         const int n = (int)(down_off_[l + 1] - down_off_[l]);
-        if (fast_down(l)) launch_pyrdown_fast(base + down_off_[l], n, tiles_dev(), l, packed_, fast_rows(l), st);
+        if (l == 0 && use_tma_) launch_pyrdown_tma(base + down_off_[l], n, tiles_dev(), tmaps_dev_.as<void>(), st);
+        else if (fast_down(l)) launch_pyrdown_fast(base + down_off_[l], n, tiles_dev(), l, packed_, fast_rows(l), st);
         else launch_pyrdown_tiles(base + down_off_[l], n, tiles_dev(), l, st);
     }
 }

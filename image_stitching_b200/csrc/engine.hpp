@@ -117,6 +117,7 @@ public:
     const std::vector<WorkItem>& warp_work() const { return warp_work_; }
     const WorkItem* warp_work_dev() const { return warp_work_dev_.as<WorkItem>(); }
     size_t pyramid_bytes() const { return arena_.used(); }
+    bool uses_tma() const { return use_tma_; }
 
 private:
     BlendGeometry g_;
@@ -125,7 +126,8 @@ private:
     int committed_ = 0;           // tiles [0, committed_) have storage
     Arena arena_;                 // fused path: one block for all tiles
     std::vector<DevBuf*> extra_;  // classic path: one allocation per late-added tile
-    DevBuf tiles_dev_, warp_work_dev_, down_work_dev_, cells_dev_, dst_buf_;
+    DevBuf tiles_dev_, warp_work_dev_, down_work_dev_, cells_dev_, dst_buf_, tmaps_dev_;
+    bool use_tma_ = false;  // level 0 -> 1 pyrDown staged by TMA (packed tiles large enough for a full box)
     std::vector<WorkItem> warp_work_;
     std::vector<std::vector<WorkItem>> down_work_;  // per level, for tiles of the last commit
     std::vector<size_t> down_off_;

@@ -49,6 +49,10 @@ void launch_warp_tiles_packed(const WorkItem* work, int n_work, const TileDev* t
 // register-rolling separable pyrDown, 2 outputs per thread (packed or planar storage)
 void launch_pyrdown_fast(const WorkItem* work, int n_work, const TileDev* tiles, int level, bool packed, int rows_per_warp,
                          cudaStream_t st);
+// TMA-staged level 0 -> 1 pyrDown of packed tiles: `tmaps` = one CUtensorMap per tile (level-0 plane), device memory
+void launch_pyrdown_tma(const WorkItem* work, int n_work, const TileDev* tiles, const void* tmaps, cudaStream_t st);
+constexpr int kTmaOutW = 64, kTmaOutH = 32;                          // outputs per CTA
+constexpr int kTmaBoxW = 2 * kTmaOutW + 8, kTmaBoxH = 2 * kTmaOutH + 3;  // 136 x 67 input box (x origin 2*ox0 - 4)
 // 2x2-quad accumulate + normalise + collapse for level < nb
 void launch_blend_quad(const DstDev& dst, const TileDev* tiles, int level, const OutDev& out, cudaStream_t st);
 void count_launch();

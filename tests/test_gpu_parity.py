@@ -176,6 +176,19 @@ def test_compose_vs_oracle(case):
     _check(out, ref)
 
 
+def test_compose_large_tiles():
+    """Tiles big enough for the TMA-staged pyrDown boxes (136 x 67) and several CTAs per tile, incl. the wrap image."""
+    rig, imgs, gains, nb = make_case("cfg2", 4, 5)
+    seams = seam_masks_oracle(rig)
+    ref = orc.compose(imgs, rig.Ks, rig.Rs, rig.scale, rig.warp, nb, gains, seams)
+    out = isb.compose(imgs, rig.Ks, rig.Rs, rig.scale, rig.warp, nb, gains, seams)
+    _check(out, ref)
+    rig, imgs, gains, nb = make_case("cfg4", 4, 5)
+    seams = seam_masks_oracle(rig)
+    _check(isb.compose(imgs, rig.Ks, rig.Rs, rig.scale, rig.warp, nb, gains, seams),
+           orc.compose(imgs, rig.Ks, rig.Rs, rig.scale, rig.warp, nb, gains, seams))
+
+
 @pytest.mark.parametrize("name", ["cfg2_d16_nb3", "cfg2_d16_nb5_checker", "cfg4_d8_nb5", "cfg3_d32_nb4"])
 def test_compose_vs_golden(name):
     cases = {"cfg2_d16_nb3": ("cfg2", 16, 3, "texture"), "cfg2_d16_nb5_checker": ("cfg2", 16, 5, "checker"),
