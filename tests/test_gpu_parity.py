@@ -252,3 +252,36 @@ def test_strip_sharding_is_bit_exact(strips):
         rows.append(r["strip_rows"])
     assert rows[0][0] == 0 and rows[-1][1] == h and all(a[1] == b[0] for a, b in zip(rows, rows[1:]))
     assert np.array_equal(outm, full["mask"]) and np.array_equal(out16, full["result16"]) and np.array_equal(out8, full["result8"])
+
+
+def test_edge_cases_tiny_single_and_empty_masks():
+    """Edge cases the domain has: a single image, tiny sources (vectorised sampler disabled), an all-zero seam mask
+    (image contributes nothing), a missing gain / seam entry, zero bands, odd panorama widths."""
+    rng = np.random.default_rng(11)
+    # (a) one tiny image, nb = 0 and nb = 2
+    K = np.array([[9, 0, 2.5], [0, 9, 2], [0, 0, 1]], np.float32)
+    R = synth.euler_yxz_to_R(0.05, 0.3, -0.02).astype(np.float32)
+    img = rng.integers(0, 256, (4, 5, 3)).astype(np.uint8)
+    for nb in (0, 2):
+        _check(isb.compose([img], [K], [R], 9.0, "spherical", nb), orc.compose([img], [K], [R], 9.0, "spherical", nb))
+    # (b) three images: one fully masked out by its seam mask, one without gain, one without seam mask
+    rig, imgs, gains, nb = make_case("cfg4", 16, 3, max_images=3)
+    seams = seam_masks_oracle(rig)
+    seams[1] = np.zeros_like(seams[1])
+    ref = orc.compose(imgs, rig.Ks, rig.Rs, rig.scale, rig.warp, nb, gains, seams)
+    out = isb.compose(imgs, rig.Ks, rig.Rs, rig.scale, rig.warp, nb, gains, seams)
+    _check(out, ref)
+    assert (out["mask"] == 0).any()  # the masked-out image leaves a hole
+    c = isb.Composer(rig.warp, rig.scale, nb)
+    c.plan(isb.cameras_from_KR(rig.Ks, rig.Rs), [(rig.W, rig.H)] * rig.n)
+    out = c.run(imgs, [gains[0], None, gains[2]], [seams[0], seams[1], None], want16=True)
+    # the oracle takes per-image optional inputs as identity gain / all-255 seam
+    g1 = np.ones((1, 1), np.float32)
+    s2 = np.full((4, 4), 255, np.uint8)
+    ref = orc.compose(imgs, rig.Ks, rig.Rs, rig.scale, rig.warp, nb, [gains[0], g1, gains[2]], [seams[0], seams[1], s2])
+    _check(out, ref)
+    # (c) cylindrical with an odd-width panorama buffer
+    rig, imgs, gains, nb = make_case("cfg4", 16, 2, max_images=2)
+    ref = orc.compose(imgs, rig.Ks, rig.Rs, rig.scale, rig.warp, nb)
+    out = isb.compose(imgs, rig.Ks, rig.Rs, rig.scale, rig.warp, nb)
+    _check(out, ref)
