@@ -66,7 +66,8 @@ class _Mask(C.Structure):
 
 class Config(C.Structure):
     _fields_ = [("warp_kind", C.c_int), ("warped_image_scale", C.c_float), ("num_bands", C.c_int),
-                ("strip_index", C.c_int), ("strip_count", C.c_int), ("cache_plan", C.c_int), ("reserved", C.c_int * 8)]
+                ("strip_index", C.c_int), ("strip_count", C.c_int), ("cache_plan", C.c_int), ("async_mode", C.c_int),
+                ("reserved", C.c_int * 7)]
 
 
 class _Pano(C.Structure):
@@ -508,13 +509,15 @@ def cameras_from_KR(Ks, Rs):
 class Composer:
     """The whole compositing loop on the GPU (isb_composer_*)."""
 
-    def __init__(self, warp="spherical", scale=1.0, num_bands=5, strip_index=0, strip_count=1, cache_plan=True):
+    def __init__(self, warp="spherical", scale=1.0, num_bands=5, strip_index=0, strip_count=1, cache_plan=True,
+                 async_mode=False):
         self.cfg = Config()
         self.cfg.warp_kind = _KIND[warp]
         self.cfg.warped_image_scale = float(scale)
         self.cfg.num_bands = int(num_bands)
         self.cfg.strip_index, self.cfg.strip_count = int(strip_index), int(strip_count)
         self.cfg.cache_plan = int(bool(cache_plan))
+        self.cfg.async_mode = int(bool(async_mode))
         self._h = C.c_void_p(lib().isb_composer_create(C.byref(self.cfg)))
         self.n = 0
 
@@ -588,6 +591,9 @@ class Composer:
         self.strip_rows = (pano.strip_y0, pano.strip_y1)
         return dict(result8=out, mask=out_mask, result16=out16, dst_roi=tuple(pano.roi_xywh),
                     strip_rows=self.strip_rows, corners=self.corners, sizes=self.sizes)
+
+    def sync(self):
+        _chk(lib().isb_composer_sync(self._h))
 
     def timings(self):
         ms = (C.c_float * 8)()

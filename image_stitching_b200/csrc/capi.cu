@@ -361,6 +361,10 @@ int isb_composer_run(isb_composer* c, const isb_image* imgs, const isb_gainmap* 
 {
     return guarded([&] { NOT_NULL(c); c->impl.run(imgs, gains, seams, n, out); });
 }
+int isb_composer_sync(isb_composer* c)
+{
+    return guarded([&] { NOT_NULL(c); c->impl.sync(); });
+}
 int isb_composer_last_timings(isb_composer* c, float* ms, int cap)
 {
     int n = 0;

@@ -966,7 +966,12 @@ void Composer::run(const isb_image* imgs, const isb_gainmap* gains, const isb_ma
     bool any_host = (out->data && !d8) || (out->mask && !dm) || (out->data16 && !d16);
     for (int i = 0; i < n && !any_host; ++i)
         if (!tiles_of_image_[i].empty() && mem_kind(imgs[i].data) == MemKind::Host) any_host = true;
-    if (any_host) ISB_CUDA(cudaStreamSynchronize(st));
+    if (any_host && !cfg_.async_mode) ISB_CUDA(cudaStreamSynchronize(st));
+}
+
+void Composer::sync()
+{
+    if (ev_init_) ISB_CUDA(cudaEventSynchronize(ev_[5]));
 }
 
 int Composer::timings(float* ms, int cap)

@@ -197,6 +197,7 @@ public:
     explicit Composer(const isb_config& cfg) : cfg_(cfg) {}
     void plan(const isb_camera* cams, const int* sizes_wh, int n, int* corners, int* sizes, int* dst_roi);
     void run(const isb_image* imgs, const isb_gainmap* gains, const isb_mask* seams, int n, isb_pano* out);
+    void sync();
     int timings(float* ms, int cap);
     void byte_model(double* S, double* M, double* Ap, double* B);
     static const char* stage_name(int i);

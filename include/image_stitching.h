@@ -201,7 +201,10 @@ typedef struct isb_config {
     int strip_index;          /* this process's strip, 0 <= strip_index < strip_count */
     int strip_count;          /* 1 = whole panorama on this GPU */
     int cache_plan;           /* !=0: keep geometry (ROIs, trig tables, tile lists) across calls with equal cameras */
-    int reserved[8];
+    int async_mode;           /* !=0: isb_composer_run() only enqueues (pinned host buffers must stay valid until
+                                 isb_composer_sync()); lets two composers on two streams overlap one step's upload with
+                                 the previous step's download */
+    int reserved[7];
 } isb_config;
 
 /* Output of isb_compose: the panorama (dst_roi_final_ size).  data/mask describe the FULL panorama buffer
@@ -224,6 +227,8 @@ ISB_API int isb_composer_plan(isb_composer* c, const isb_camera* cams, const int
 /* Runs the loop on the planned geometry. gains / seam_masks may be NULL. */
 ISB_API int isb_composer_run(isb_composer* c, const isb_image* imgs, const isb_gainmap* gains, const isb_mask* seam_masks,
                              int n, isb_pano* out);
+/* waits for the last isb_composer_run() of this composer (needed only in async_mode) */
+ISB_API int isb_composer_sync(isb_composer* c);
 /* device time (ms) of the last run split by stage; names via isb_composer_stage_name; returns #stages */
 ISB_API int isb_composer_last_timings(isb_composer* c, float* ms, int capacity);
 ISB_API const char* isb_composer_stage_name(int stage);
