@@ -285,3 +285,26 @@ def test_edge_cases_tiny_single_and_empty_masks():
     ref = orc.compose(imgs, rig.Ks, rig.Rs, rig.scale, rig.warp, nb)
     out = isb.compose(imgs, rig.Ks, rig.Rs, rig.scale, rig.warp, nb)
     _check(out, ref)
+
+
+def test_cfg4_cameras_through_serializer(tmp_path):
+    """BASELINE config 4: fixed cameras written to / loaded from cams.data (lossy 6-digit text, serializer.cpp:113-167);
+    the composer must agree with the oracle on the LOADED cameras, frame after frame, with the cached plan."""
+    rig, imgs, gains, nb = make_case("cfg4", 8, 5)
+    path = str(tmp_path / "cams.data")
+    isb.serializeCameraParams(isb.cameras_from_KR(rig.Ks, rig.Rs), path)
+    cams = isb.deserializeCameraParams(path)
+    Ks = [c.K() for c in cams]
+    Rs = [np.array(list(c.R), np.float32).reshape(3, 3) for c in cams]
+    assert not all(np.array_equal(a, b) for a, b in zip(Rs, rig.Rs))  # the text format really is lossy
+    seams = []
+    src = synth.seam_source_mask(rig.W, rig.H)
+    for K, R in zip(Ks, Rs):
+        Ksm, ss = synth.seam_camera(K, rig.scale)
+        seams.append(orc.warp(rig.warp, ss, src, Ksm, R, orc.NEAREST, 0)[1])
+    c = isb.Composer(rig.warp, rig.scale, nb, cache_plan=True)
+    for frame in range(3):  # new pixels each frame, geometry / masks / gains fixed
+        frames = [synth.make_image(100 * frame + i, rig.W, rig.H) for i in range(rig.n)]
+        c.plan(cams, [(rig.W, rig.H)] * rig.n)
+        out = c.run(frames, gains, seams, want16=True)
+        _check(out, orc.compose(frames, Ks, Rs, rig.scale, rig.warp, nb, gains, seams))
