@@ -95,6 +95,8 @@ def lib():
     L.isb_warper_create.argtypes = [C.c_int, C.c_float]
     L.isb_warper_set_scale.argtypes = [C.c_void_p, C.c_float]
     L.isb_num_bands_for.argtypes = [C.c_int, C.c_int, C.c_float]
+    L.isb_resize_linear_exact.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int, C.c_int,
+                                          C.c_size_t, C.c_double, C.c_double]
     L.isb_quat_slerp.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
     L.isb_quat_from_axis_angle.argtypes = [C.c_void_p, C.c_double, C.c_void_p]
     for f in ("isb_warper_destroy", "isb_compensator_destroy", "isb_blender_destroy", "isb_composer_destroy"):
@@ -411,6 +413,36 @@ class BlocksGainCompensator:
         _chk(lib().isb_compensator_apply(self._h, int(index), c, img.ctypes.data_as(C.c_void_p), w, h,
                                          C.c_size_t(w * 3), None, C.c_size_t(0)))
         return img
+
+
+ROTATE_90_CLOCKWISE, ROTATE_180 = 0, 1
+
+
+def rotate(src, rotate_code):
+    """cv2.rotate(src, ROTATE_90_CLOCKWISE | ROTATE_180) for 8UC1 / 8UC3 (image_stitching.cpp:1093-1103)."""
+    src = np.ascontiguousarray(src, np.uint8)
+    h, w = src.shape[:2]
+    ch = 1 if src.ndim == 2 else src.shape[2]
+    shape = (w, h) if rotate_code == ROTATE_90_CLOCKWISE else (h, w)
+    dst = np.empty(shape if src.ndim == 2 else shape + (ch,), np.uint8)
+    _chk(lib().isb_rotate(src.ctypes.data_as(C.c_void_p), w, h, ch, C.c_size_t(w * ch), int(rotate_code),
+                          dst.ctypes.data_as(C.c_void_p), C.c_size_t(shape[1] * ch)))
+    return dst
+
+
+def resize_linear_exact(src, dsize=None, fx=0.0, fy=0.0):
+    """cv2.resize(src, dsize, fx=fx, fy=fy, interpolation=INTER_LINEAR_EXACT) for 8UC1 / 8UC3."""
+    src = np.ascontiguousarray(src, np.uint8)
+    h, w = src.shape[:2]
+    ch = 1 if src.ndim == 2 else src.shape[2]
+    if dsize is None:
+        dw, dh = int(np.rint(w * fx)), int(np.rint(h * fy))  # cvRound
+    else:
+        dw, dh, fx, fy = int(dsize[0]), int(dsize[1]), 0.0, 0.0
+    dst = np.empty((dh, dw) if src.ndim == 2 else (dh, dw, ch), np.uint8)
+    _chk(lib().isb_resize_linear_exact(src.ctypes.data_as(C.c_void_p), w, h, ch, w * ch, dst.ctypes.data_as(C.c_void_p),
+                                       dw, dh, dw * ch, float(fx), float(fy)))
+    return dst
 
 
 def seam_mask_apply(seam_mask, mask_warped):

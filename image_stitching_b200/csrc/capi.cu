@@ -279,6 +279,16 @@ int isb_seam_mask_apply(const uint8_t* seam, int mw, int mh, size_t spitch, uint
     return guarded([&] { seam_mask_apply(seam, mw, mh, spitch, mask, w, h, pitch); });
 }
 
+int isb_rotate(const uint8_t* src, int w, int h, int ch, size_t spitch, int code, uint8_t* dst, size_t dpitch)
+{
+    return guarded([&] { rotate_image(src, w, h, ch, spitch, code, dst, dpitch); });
+}
+int isb_resize_linear_exact(const uint8_t* src, int sw, int sh, int ch, size_t spitch, uint8_t* dst, int dw, int dh,
+                            size_t dpitch, double fx, double fy)
+{
+    return guarded([&] { resize_linear_exact(src, sw, sh, ch, spitch, dst, dw, dh, dpitch, fx, fy); });
+}
+
 // ---- blender --------------------------------------------------------------------------------------
 int isb_result_roi(const int* corners, const int* sizes, int n, int rect[4])
 {

@@ -549,6 +549,70 @@ void seam_mask_apply(const uint8_t* seam, int mw, int mh, size_t spitch, uint8_t
     ISB_CUDA(cudaStreamSynchronize(st));
 }
 
+void rotate_image(const uint8_t* src, int w, int h, int ch, size_t spitch, int code, uint8_t* dst, size_t dpitch)
+{
+    require_device();
+    if (!src || !dst) throw Error(ISB_ERR_NULL_PTR, "src/dst are null");
+    ISB_ASSERT(w > 0 && h > 0 && (ch == 1 || ch == 3) && (code == 0 || code == 1));
+    const int dw = code == 0 ? h : w, dh = code == 0 ? w : h;
+    ISB_ASSERT(spitch >= (size_t)w * ch && dpitch >= (size_t)dw * ch);
+    cudaStream_t st = current_stream();
+    DevBuf sb, db;
+    const uint8_t* s = src;
+    size_t sp = spitch;
+    if (mem_kind(src) != MemKind::Device) {
+        sp = (size_t)w * ch;
+        void* p = sb.ensure(sp * h);
+        copy2d(p, sp, src, spitch, sp, h, st);
+        s = static_cast<const uint8_t*>(p);
+    }
+    const bool ddev = mem_kind(dst) == MemKind::Device;
+    uint8_t* d = dst;
+    size_t dp = dpitch;
+    if (!ddev) {
+        dp = (size_t)dw * ch;
+        d = static_cast<uint8_t*>(db.ensure(dp * dh));
+    }
+    launch_rotate(s, w, h, ch, (long long)sp, code, d, (long long)dp, st);
+    if (!ddev) copy2d(dst, dpitch, d, dp, (size_t)dw * ch, dh, st);
+    ISB_CUDA(cudaStreamSynchronize(st));
+}
+
+void resize_linear_exact(const uint8_t* src, int sw, int sh, int ch, size_t spitch, uint8_t* dst, int dw, int dh, size_t dpitch,
+                         double fx, double fy)
+{
+    require_device();
+    if (!src || !dst) throw Error(ISB_ERR_NULL_PTR, "src/dst are null");
+    ISB_ASSERT(sw > 0 && sh > 0 && dw > 0 && dh > 0 && (ch == 1 || ch == 3));
+    ISB_ASSERT(spitch >= (size_t)sw * ch && dpitch >= (size_t)dw * ch);
+    cudaStream_t st = current_stream();
+    std::vector<uint32_t> tx, ty;
+    build_linear_exact_table(sw, dw, tx, fx);
+    build_linear_exact_table(sh, dh, ty, fy);
+    DevBuf sb, db, tb;
+    uint32_t* t = static_cast<uint32_t*>(tb.ensure((tx.size() + ty.size()) * sizeof(uint32_t)));
+    ISB_CUDA(cudaMemcpyAsync(t, tx.data(), tx.size() * 4, cudaMemcpyHostToDevice, st));
+    ISB_CUDA(cudaMemcpyAsync(t + tx.size(), ty.data(), ty.size() * 4, cudaMemcpyHostToDevice, st));
+    const uint8_t* s = src;
+    size_t sp = spitch;
+    if (mem_kind(src) != MemKind::Device) {
+        sp = (size_t)sw * ch;
+        void* p = sb.ensure(sp * sh);
+        copy2d(p, sp, src, spitch, sp, sh, st);
+        s = static_cast<const uint8_t*>(p);
+    }
+    const bool ddev = mem_kind(dst) == MemKind::Device;
+    uint8_t* d = dst;
+    size_t dp = dpitch;
+    if (!ddev) {
+        dp = (size_t)dw * ch;
+        d = static_cast<uint8_t*>(db.ensure(dp * dh));
+    }
+    launch_resize_exact(s, sw, sh, ch, (long long)sp, t, t + tx.size(), d, dw, dh, (long long)dp, st);
+    if (!ddev) copy2d(dst, dpitch, d, dp, (size_t)dw * ch, dh, st);
+    ISB_CUDA(cudaStreamSynchronize(st));
+}
+
 // ------------------------------------------------------------------------------------------------
 // Blender (classic prepare / feed / blend surface)
 // ------------------------------------------------------------------------------------------------

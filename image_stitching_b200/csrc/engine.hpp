@@ -172,6 +172,11 @@ private:
     PinBuf pin_;
 };
 
+// ingest pre-steps (image_stitching.cpp:1093-1103, 1143-1146)
+void rotate_image(const uint8_t* src, int w, int h, int ch, size_t spitch, int code, uint8_t* dst, size_t dpitch);
+void resize_linear_exact(const uint8_t* src, int sw, int sh, int ch, size_t spitch, uint8_t* dst, int dw, int dh, size_t dpitch,
+                         double fx, double fy);
+
 void seam_mask_apply(const uint8_t* seam, int mw, int mh, size_t spitch, uint8_t* mask, int w, int h, size_t pitch);
 
 class Blender {

@@ -140,10 +140,12 @@ void build_trig_tables(const Projector& p, const Rect& roi, std::vector<Float2>&
     }
 }
 
-void build_linear_exact_table(int src_n, int dst_n, std::vector<uint32_t>& tab)
+void build_linear_exact_table(int src_n, int dst_n, std::vector<uint32_t>& tab, double inv_scale)
 {
     tab.resize(dst_n);
-    const double scale = (double)src_n / dst_n;
+    // cv::resize: inv_scale = fx when given, else dst/src; the bit-exact path then uses scale = 1 / inv_scale
+    if (inv_scale <= 0) inv_scale = (double)dst_n / src_n;
+    const double scale = 1.0 / inv_scale;
     for (int d = 0; d < dst_n; ++d) {
         const double f = (d + 0.5) * scale - 0.5;
         int s = (int)std::floor(f);

@@ -36,7 +36,7 @@ struct Float2 { float a, b; };
 void build_trig_tables(const Projector& p, const Rect& roi, std::vector<Float2>& col, std::vector<Float2>& row);
 
 // cv::resize(INTER_LINEAR_EXACT) 8U coefficients per destination index: (ofs << 16) | alpha(0..256)
-void build_linear_exact_table(int src_n, int dst_n, std::vector<uint32_t>& tab);
+void build_linear_exact_table(int src_n, int dst_n, std::vector<uint32_t>& tab, double inv_scale = 0.0);
 // cv::resize(INTER_LINEAR) f32 coefficients per destination index: ofs and fraction.
 // `clamp_frac`: horizontal pass zeroes the fraction at the borders, the vertical pass does not.
 struct LinCoef { int ofs; float frac; };

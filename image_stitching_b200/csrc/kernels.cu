@@ -173,6 +173,65 @@ void launch_pack_tile(const TileDev* tile_dev, const TileDev& tile_host, const i
 }
 
 // ------------------------------------------------------------------------------------------------
+// ingest pre-steps: cv::rotate(90 CW | 180) and cv::resize(INTER_LINEAR_EXACT), 8U x {1,3} channels
+// ------------------------------------------------------------------------------------------------
+template <int CH>
+__global__ void __launch_bounds__(256) rotate_kernel(const uint8_t* __restrict__ src, int w, int h, long long spitch, int code,
+                                                     uint8_t* __restrict__ dst, long long dpitch)
+{
+    // one thread per DESTINATION pixel (coalesced stores); dst is (h x w) for 90 CW, (w x h) for 180
+    const int dw = code == 0 ? h : w, dh = code == 0 ? w : h;
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= dw || y >= dh) return;
+    const int sx = code == 0 ? y : w - 1 - x, sy = code == 0 ? h - 1 - x : h - 1 - y;
+    const uint8_t* p = src + sy * spitch + sx * CH;
+    uint8_t* q = dst + y * dpitch + x * CH;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) q[c] = p[c];
+}
+
+void launch_rotate(const uint8_t* src, int w, int h, int ch, long long spitch, int code, uint8_t* dst, long long dpitch,
+                   cudaStream_t st)
+{
+    const int dw = code == 0 ? h : w, dh = code == 0 ? w : h;
+    dim3 grid((dw + 31) / 32, (dh + 7) / 8);
+    if (ch == 3) rotate_kernel<3><<<grid, 256, 0, st>>>(src, w, h, spitch, code, dst, dpitch);
+    else rotate_kernel<1><<<grid, 256, 0, st>>>(src, w, h, spitch, code, dst, dpitch);
+    ISB_COUNT_LAUNCH();
+}
+
+template <int CH>
+__global__ void __launch_bounds__(256) resize_exact_kernel(const uint8_t* __restrict__ src, int sw, int sh, long long spitch,
+                                                           const uint32_t* __restrict__ tx, const uint32_t* __restrict__ ty,
+                                                           uint8_t* __restrict__ dst, int dw, int dh, long long dpitch)
+{
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= dw || y >= dh) return;
+    const uint32_t cx = tx[x], cy = ty[y];
+    const int c0 = cx >> 16, ax = cx & 0xffff, r0 = cy >> 16, ay = cy & 0xffff;
+    const int c1 = min(c0 + 1, sw - 1), r1 = min(r0 + 1, sh - 1);
+    const uint8_t* p0 = src + r0 * spitch;
+    const uint8_t* p1 = src + r1 * spitch;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+        const int h0 = p0[c0 * CH + c] * (256 - ax) + p0[c1 * CH + c] * ax;
+        const int h1 = p1[c0 * CH + c] * (256 - ax) + p1[c1 * CH + c] * ax;
+        dst[y * dpitch + x * CH + c] = (uint8_t)((h0 * (256 - ay) + h1 * ay + 32768) >> 16);
+    }
+}
+
+void launch_resize_exact(const uint8_t* src, int sw, int sh, int ch, long long spitch, const uint32_t* tx, const uint32_t* ty,
+                         uint8_t* dst, int dw, int dh, long long dpitch, cudaStream_t st)
+{
+    dim3 grid((dw + 31) / 32, (dh + 7) / 8);
+    if (ch == 3) resize_exact_kernel<3><<<grid, 256, 0, st>>>(src, sw, sh, spitch, tx, ty, dst, dw, dh, dpitch);
+    else resize_exact_kernel<1><<<grid, 256, 0, st>>>(src, sw, sh, spitch, tx, ty, dst, dw, dh, dpitch);
+    ISB_COUNT_LAUNCH();
+}
+
+// ------------------------------------------------------------------------------------------------
 // plan-time: count valid warped pixels (M of the byte model)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) count_valid_kernel(const ImageDev* __restrict__ imgs,

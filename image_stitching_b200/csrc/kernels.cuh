@@ -26,6 +26,14 @@ void launch_seam_and(const uint8_t* dil, int mw, int mh, const uint32_t* mx, con
 void launch_pack_tile(const TileDev* tile_dev, const TileDev& tile_host, const int16_t* img, long long ipitch,
                       const uint8_t* mask, long long mpitch, cudaStream_t st);
 
+// ingest pre-steps of the compositing loop (image_stitching.cpp:1093-1103, 1143-1146)
+// cv::rotate: code 0 = ROTATE_90_CLOCKWISE (dst is h x w), 1 = ROTATE_180
+void launch_rotate(const uint8_t* src, int w, int h, int ch, long long spitch, int code, uint8_t* dst, long long dpitch,
+                   cudaStream_t st);
+// cv::resize(INTER_LINEAR_EXACT) on 8U, 1 or 3 channels; tx/ty = per-destination (ofs << 16) | alpha tables
+void launch_resize_exact(const uint8_t* src, int sw, int sh, int ch, long long spitch, const uint32_t* tx, const uint32_t* ty,
+                         uint8_t* dst, int dw, int dh, long long dpitch, cudaStream_t st);
+
 // ---- batched pyramid pipeline -----------------------------------------------------------------
 // number of valid (mask != 0) warped pixels of every image -> counts[img] (unsigned long long)
 void launch_count_valid(const ImageDev* imgs_dev, int n_img, const int* roi_w_host, const int* roi_h_host,

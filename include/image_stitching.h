@@ -159,6 +159,21 @@ ISB_API int isb_seam_mask_apply(const uint8_t* seam_mask, int seam_w, int seam_h
                                 uint8_t* mask_warped, int w, int h, size_t pitch);
 
 /* ============================================================================================
+ * Ingest pre-steps of the loop: the rotation every decoded image gets and the
+ * compose-scale down-sizing.  Both are bit-exact integer operations.
+ * ============================================================================================ */
+enum { ISB_ROTATE_90_CLOCKWISE = 0, ISB_ROTATE_180 = 1 };      /* cv::ROTATE_90_CLOCKWISE / cv::ROTATE_180 */
+/* rotate(full_img, tmp, ROTATE_90_CLOCKWISE | ROTATE_180)  (image_stitching.cpp:1093-1103, 569-581).
+ * dst is (src_h x src_w) pixels wide x high for ROTATE_90_CLOCKWISE, (src_w x src_h) for ROTATE_180. */
+ISB_API int isb_rotate(const uint8_t* src, int src_w, int src_h, int channels, size_t src_pitch, int rotate_code,
+                       uint8_t* dst, size_t dst_pitch);
+/* cv::resize(full_img, img, Size(), compose_scale, compose_scale, INTER_LINEAR_EXACT)  (image_stitching.cpp:1143-1146).
+ * Pass fx, fy > 0 for the scale-factor form (dst_w = cvRound(src_w * fx), which the caller computes) or fx = fy = 0
+ * for the dsize form (as used for the seam mask, :1170). */
+ISB_API int isb_resize_linear_exact(const uint8_t* src, int src_w, int src_h, int channels, size_t src_pitch, uint8_t* dst,
+                                    int dst_w, int dst_h, size_t dst_pitch, double fx, double fy);
+
+/* ============================================================================================
  * cv::detail::MultiBandBlender  (image_stitching.cpp:1173-1225)
  * ============================================================================================ */
 typedef struct isb_blender isb_blender;

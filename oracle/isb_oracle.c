@@ -341,9 +341,12 @@ ORC_API void orc_dilate3x3_8u(const uint8_t* src, int w, int h, uint8_t* dst)
         }
 }
 
-static void linear_exact_coeffs(int sn, int dn, int* ofs, int* alpha)
+/* inv_scale = fx (the fx/fy form of cv::resize) or 0 for the dsize form, where OpenCV sets inv_scale = dn / sn;
+ * either way the bit-exact resize works with scale = 1 / inv_scale (resize.cpp, interpolationLinear). */
+static void linear_exact_coeffs(int sn, int dn, double inv_scale, int* ofs, int* alpha)
 {
-    double scale = (double)sn / dn;
+    if (inv_scale <= 0) inv_scale = (double)dn / sn;
+    double scale = 1.0 / inv_scale;
     for (int d = 0; d < dn; ++d) {
         double f = (d + 0.5) * scale - 0.5;
         int s = (int)floor(f);
@@ -355,25 +358,46 @@ static void linear_exact_coeffs(int sn, int dn, int* ofs, int* alpha)
     }
 }
 
-ORC_API void orc_resize_linear_exact_8u(const uint8_t* src, int sw, int sh, uint8_t* dst, int dw, int dh)
+/* cv::resize(INTER_LINEAR_EXACT) on 8U with `ch` interleaved channels; fx = fy = 0 selects the dsize form */
+ORC_API void orc_resize_linear_exact_8u_ex(const uint8_t* src, int sw, int sh, int ch, uint8_t* dst, int dw, int dh,
+                                           double fx, double fy)
 {
     int* xo = (int*)malloc(sizeof(int) * dw * 2);
     int* xa = xo + dw;
     int* yo = (int*)malloc(sizeof(int) * dh * 2);
     int* ya = yo + dh;
-    linear_exact_coeffs(sw, dw, xo, xa);
-    linear_exact_coeffs(sh, dh, yo, ya);
+    linear_exact_coeffs(sw, dw, fx, xo, xa);
+    linear_exact_coeffs(sh, dh, fy, yo, ya);
     for (int y = 0; y < dh; ++y) {
         int s0 = yo[y], s1 = s0 + 1 < sh ? s0 + 1 : s0;
         for (int x = 0; x < dw; ++x) {
             int c0 = xo[x], c1 = c0 + 1 < sw ? c0 + 1 : c0;
-            int r0 = src[(size_t)s0 * sw + c0] * (256 - xa[x]) + src[(size_t)s0 * sw + c1] * xa[x];
-            int r1 = src[(size_t)s1 * sw + c0] * (256 - xa[x]) + src[(size_t)s1 * sw + c1] * xa[x];
-            dst[(size_t)y * dw + x] = (uint8_t)((r0 * (256 - ya[y]) + r1 * ya[y] + 32768) >> 16);
+            for (int c = 0; c < ch; ++c) {
+                int r0 = src[((size_t)s0 * sw + c0) * ch + c] * (256 - xa[x]) + src[((size_t)s0 * sw + c1) * ch + c] * xa[x];
+                int r1 = src[((size_t)s1 * sw + c0) * ch + c] * (256 - xa[x]) + src[((size_t)s1 * sw + c1) * ch + c] * xa[x];
+                dst[((size_t)y * dw + x) * ch + c] = (uint8_t)((r0 * (256 - ya[y]) + r1 * ya[y] + 32768) >> 16);
+            }
         }
     }
     free(xo);
     free(yo);
+}
+
+ORC_API void orc_resize_linear_exact_8u(const uint8_t* src, int sw, int sh, uint8_t* dst, int dw, int dh)
+{
+    orc_resize_linear_exact_8u_ex(src, sw, sh, 1, dst, dw, dh, 0, 0);
+}
+
+/* cv::rotate: code 0 = ROTATE_90_CLOCKWISE, 1 = ROTATE_180 (image_stitching.cpp:1093-1103).  dst is h x w for code 0. */
+ORC_API void orc_rotate_8u(const uint8_t* src, int w, int h, int ch, int code, uint8_t* dst)
+{
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x)
+            for (int c = 0; c < ch; ++c) {
+                uint8_t v = src[((size_t)y * w + x) * ch + c];
+                if (code == 0) dst[((size_t)x * h + (h - 1 - y)) * ch + c] = v;       /* (x, y) -> (h-1-y, x) */
+                else dst[((size_t)(h - 1 - y) * w + (w - 1 - x)) * ch + c] = v;
+            }
 }
 
 /* ---- A.7 gain map: cv::resize(f32, INTER_LINEAR) + multiply -------------------------- */

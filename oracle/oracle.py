@@ -107,6 +107,26 @@ def resize_linear_exact(m, dw, dh):
     return o
 
 
+def resize_linear_exact_ex(img, dw, dh, fx=0.0, fy=0.0):
+    img = np.ascontiguousarray(img, np.uint8)
+    ch = 1 if img.ndim == 2 else img.shape[2]
+    o = np.empty((dh, dw) if img.ndim == 2 else (dh, dw, ch), np.uint8)
+    lib().orc_resize_linear_exact_8u_ex(_p(img), img.shape[1], img.shape[0], ch, _p(o), int(dw), int(dh), C.c_double(fx),
+                                        C.c_double(fy))
+    return o
+
+
+def rotate(img, code):
+    """code 0 = ROTATE_90_CLOCKWISE, 1 = ROTATE_180"""
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape[:2]
+    ch = 1 if img.ndim == 2 else img.shape[2]
+    shape = (w, h) if code == 0 else (h, w)
+    o = np.empty(shape if img.ndim == 2 else shape + (ch,), np.uint8)
+    lib().orc_rotate_8u(_p(img), w, h, ch, int(code), _p(o))
+    return o
+
+
 def resize_linear_f32(g, dw, dh):
     g = _f32(g)
     o = np.empty((dh, dw), np.float32)

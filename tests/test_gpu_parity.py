@@ -308,3 +308,39 @@ def test_cfg4_cameras_through_serializer(tmp_path):
         c.plan(cams, [(rig.W, rig.H)] * rig.n)
         out = c.run(frames, gains, seams, want16=True)
         _check(out, orc.compose(frames, Ks, Rs, rig.scale, rig.warp, nb, gains, seams))
+
+
+def test_ingest_presteps_rotate_and_resize():
+    """rotate(90CW/180) + resize(compose_scale, INTER_LINEAR_EXACT), bit-exact."""
+    rng = np.random.default_rng(8)
+    for shape in [(37, 53, 3), (64, 40), (1, 7, 3), (300, 201, 3)]:
+        a = rng.integers(0, 256, shape).astype(np.uint8)
+        assert np.array_equal(isb.rotate(a, isb.ROTATE_90_CLOCKWISE), orc.rotate(a, 0))
+        assert np.array_equal(isb.rotate(a, isb.ROTATE_180), orc.rotate(a, 1))
+    img = synth.make_image(5, 530, 370)
+    for fs in (0.3651483716701107, 0.5, 0.71, 0.123, 1.3):
+        out = isb.resize_linear_exact(img, fx=fs, fy=fs)
+        assert np.array_equal(out, orc.resize_linear_exact_ex(img, out.shape[1], out.shape[0], fs, fs))
+    for (dw, dh) in [(194, 135), (531, 371), (1000, 37), (53, 700)]:
+        assert np.array_equal(isb.resize_linear_exact(img, (dw, dh)), orc.resize_linear_exact_ex(img, dw, dh))
+    m = rng.integers(0, 256, (33, 57)).astype(np.uint8)
+    assert np.array_equal(isb.resize_linear_exact(m, (453, 260)), orc.resize_linear_exact(m, 453, 260))
+
+
+def test_seam_scale_auxiliary_warp():
+    """SURVEY.md 8(f) rank 1 (image_stitching.cpp:973-995): the low-resolution warp of every image and mask that feeds
+    the (CPU) exposure compensator and seam finder - same warper, K scaled by seam_work_aspect, scale * aspect."""
+    rig, imgs, _, _ = make_case("cfg2", 4, 5, max_images=3)
+    aspect = 1.0 / synth.SEAM_DIV
+    for img, K, R in zip(imgs, rig.Ks, rig.Rs):
+        small = isb.resize_linear_exact(img, fx=aspect, fy=aspect)   # seam_scale resize (:604-622)
+        assert np.array_equal(small, orc.resize_linear_exact_ex(img, small.shape[1], small.shape[0], aspect, aspect))
+        Ks, ss = synth.seam_camera(K, rig.scale)
+        w = isb.RotationWarper(rig.warp, ss)
+        c1, a = w.warp(small, Ks, R, isb.INTER_LINEAR, isb.BORDER_REFLECT)
+        c2, b = orc.warp(rig.warp, ss, small, Ks, R, orc.LINEAR, 1)
+        assert c1 == c2 and np.array_equal(a, b)
+        m = np.full(small.shape[:2], 255, np.uint8)
+        c1, a = w.warp(m, Ks, R, isb.INTER_NEAREST, isb.BORDER_CONSTANT)
+        c2, b = orc.warp(rig.warp, ss, m, Ks, R, orc.NEAREST, 0)
+        assert c1 == c2 and np.array_equal(a, b)

@@ -130,3 +130,20 @@ def test_compose(cv2_parity, case):
     assert ref["corners"] == out["corners"] and ref["sizes"] == out["sizes"] and ref["dst_roi"] == out["dst_roi"]
     assert np.array_equal(ref["mask"], out["mask"])
     assert np.array_equal(ref["result16"], out["result16"])
+
+
+def test_ingest_presteps(cv2_parity):
+    """rotate(90CW / 180) and resize(INTER_LINEAR_EXACT) in both the dsize and the fx/fy form (image_stitching.cpp:1093-1146)."""
+    cv2 = cv2_parity
+    rng = np.random.default_rng(8)
+    for shape in [(37, 53, 3), (64, 40), (1, 7, 3)]:
+        a = rng.integers(0, 256, shape).astype(np.uint8)
+        assert np.array_equal(cv2.rotate(a, cv2.ROTATE_90_CLOCKWISE), orc.rotate(a, 0))
+        assert np.array_equal(cv2.rotate(a, cv2.ROTATE_180), orc.rotate(a, 1))
+    img = rng.integers(0, 256, (370, 530, 3)).astype(np.uint8)
+    for fs in (0.3651483716701107, 0.5, 0.71, 0.123, 1.3):
+        ref = cv2.resize(img, None, fx=fs, fy=fs, interpolation=cv2.INTER_LINEAR_EXACT)
+        assert np.array_equal(ref, orc.resize_linear_exact_ex(img, ref.shape[1], ref.shape[0], fs, fs))
+    for (dw, dh) in [(194, 135), (531, 371), (1000, 37), (53, 700)]:
+        ref = cv2.resize(img, (dw, dh), interpolation=cv2.INTER_LINEAR_EXACT)
+        assert np.array_equal(ref, orc.resize_linear_exact_ex(img, dw, dh))
