@@ -89,23 +89,6 @@ void* DevBuf::ensure(size_t bytes)
     return p_;
 }
 
-PinBuf::~PinBuf()
-{
-    if (p_) cudaFreeHost(p_);
-}
-void* PinBuf::ensure(size_t bytes)
-{
-    if (bytes <= cap_ && p_) return p_;
-    if (p_) {
-        ISB_CUDA(cudaFreeHost(p_));
-        p_ = nullptr;
-        cap_ = 0;
-    }
-    ISB_CUDA(cudaMallocHost(&p_, std::max<size_t>(bytes, 256)));
-    cap_ = std::max<size_t>(bytes, 256);
-    return p_;
-}
-
 // copy a (rows x row_bytes) block between any two memory kinds on `st`
 static void copy2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t row_bytes, size_t rows,
                    cudaStream_t st)

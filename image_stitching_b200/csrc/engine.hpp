@@ -48,19 +48,6 @@ private:
     size_t cap_ = 0;
 };
 
-// growable pinned host allocation used to stage small descriptor uploads
-class PinBuf {
-public:
-    PinBuf() = default;
-    PinBuf(const PinBuf&) = delete;
-    PinBuf& operator=(const PinBuf&) = delete;
-    ~PinBuf();
-    void* ensure(size_t bytes);
-private:
-    void* p_ = nullptr;
-    size_t cap_ = 0;
-};
-
 // bump allocator over one device block; sized by a dry run, then replayed
 class Arena {
 public:
@@ -131,7 +118,6 @@ private:
     std::vector<WorkItem> warp_work_;
     std::vector<std::vector<WorkItem>> down_work_;  // per level, for tiles of the last commit
     std::vector<size_t> down_off_;
-    PinBuf pin_;
     DstDev dst_{};
     bool packed_ = false;
 public:
@@ -154,7 +140,6 @@ private:
     int kind_;
     float scale_;
     DevBuf src_, dst_, tab_, xm_, ym_;
-    PinBuf pin_;
 };
 
 class Compensator {
@@ -169,7 +154,6 @@ private:
     std::vector<std::vector<float>> gains_;
     std::vector<int> gw_, gh_;
     DevBuf img_, aux_;
-    PinBuf pin_;
 };
 
 // ingest pre-steps (image_stitching.cpp:1093-1103, 1143-1146)
@@ -219,7 +203,6 @@ private:
     Arena tables_;              // trig tables (static per plan)
     Arena dyn_;                 // per-run uploads: sources, gains, seam masks, their coefficient tables
     DevBuf imgs_dev_, counts_dev_, out8_, outm_, out16_;
-    PinBuf pin_, pin_tab_;
     std::vector<unsigned long long> valid_counts_;
     cudaEvent_t ev_[8] = {};
     bool ev_init_ = false;

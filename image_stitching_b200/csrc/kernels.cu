@@ -1,4 +1,5 @@
-// kernels.cu - hand-written sm_100a kernels of the compositing hot path.
+// kernels.cu - kernels of the per-object API (warp, buildMaps, gain, seam mask, feed packing, rotate, resize) and the
+// generic (any size / any storage) pyramid kernels; the fused composer's fast path lives in kernels_fast.cu.
 //
 // Arithmetic contract (each item pinned against OpenCV 4.13 by the oracle):
 //  * every float op of the inverse map / gain / weight pyramid rounds to binary32 on its own
@@ -272,72 +273,7 @@ void launch_count_valid(const ImageDev* imgs_dev, int n_img, const int* roi_w_ho
 }
 
 // ------------------------------------------------------------------------------------------------
-// kernel 1: fused warp -> level 0 of the per-image pyramids
-//   G0 = REFLECT-padded  sat_u8(rint(bilinear(src at R*K^-1 map) * gain))  as 16S, planar
-//   W0 = (seam_up & valid) / 255 inside the ROI, 0 in the padding
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) warp_tiles_kernel(const WorkItem* __restrict__ work, const TileDev* __restrict__ tiles,
-                                                         const ImageDev* __restrict__ imgs)
-{
-    const WorkItem wi = work[blockIdx.x];
-    const TileDev& T = tiles[wi.tile];
-    const ImageDev& I = imgs[T.img];
-    const int x = wi.bx * kWarpBlockW + (threadIdx.x & 63);
-    if (x >= T.w) return;
-    const int rx0 = x - T.left;
-    const bool in_x = (unsigned)rx0 < (unsigned)I.roi_w;
-    const int rx = reflect(rx0, I.roi_w);
-    const F2 col = I.col[rx];
-    const bool has_gain = I.gain != nullptr, has_seam = I.seam != nullptr;
-    LinCoefDev gx{0, 0.f};
-    uint32_t mx = 0;
-    if (has_gain) gx = I.gx[rx];
-    if (has_seam) mx = I.mx[rx];
-    const float inv255 = (float)(1. / 255.);
-    const int ybase = wi.by * kWarpBlockH + (threadIdx.x >> 6);
-    int16_t* __restrict__ G = T.G[0];
-    float* __restrict__ W = T.W[0];
-    const int gp = T.gpitch[0], wp = T.wpitch[0];
-    const long long plane = T.gplane[0];
-#pragma unroll 2
-    for (int k = 0; k < kWarpBlockH / 4; ++k) {
-        const int y = ybase + 4 * k;
-        if (y >= T.h) break;
-        const int ry0 = y - T.top;
-        const bool in = in_x && (unsigned)ry0 < (unsigned)I.roi_h;
-        const int ry = reflect(ry0, I.roi_h);
-        const XY m = inverse_map(I.kr, col, I.row[ry]);
-        int v[3];
-        sample_linear<3, true>(I, m, v);
-        if (has_gain) {
-            const float g = gain_at(I, gx, I.gy[ry]);
-#pragma unroll
-            for (int c = 0; c < 3; ++c) v[c] = sat_u8(cv_round(__fmul_rn((float)v[c], g)));
-        }
-        float w = 0.f;
-        if (in) {
-            int ix, iy;
-            int mval = nearest_inside(I, m, ix, iy) ? 255 : 0;
-            if (has_seam && mval) mval &= seam_at(I.seam, I.mw, I.mh, mx, I.my[ry]);
-            w = __fmul_rn((float)mval, inv255);
-        }
-        const long long o = (long long)y * gp + x;
-        G[o] = (int16_t)v[0];
-        G[o + plane] = (int16_t)v[1];
-        G[o + 2 * plane] = (int16_t)v[2];
-        W[(long long)y * wp + x] = w;
-    }
-}
-
-void launch_warp_tiles(const WorkItem* work, int n_work, const TileDev* tiles, const ImageDev* imgs, cudaStream_t st)
-{
-    if (n_work <= 0) return;
-    warp_tiles_kernel<<<n_work, 256, 0, st>>>(work, tiles, imgs);
-    ISB_COUNT_LAUNCH();
-}
-
-// ------------------------------------------------------------------------------------------------
-// kernel 2: pyrDown of both pyramids, one level
+// kernel 2 (generic): pyrDown of both pyramids, one level, any size / storage (odd coarse levels, tiny tiles)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) pyrdown_tiles_kernel(const WorkItem* __restrict__ work,
                                                             const TileDev* __restrict__ tiles, int l)
@@ -395,7 +331,7 @@ void launch_pyrdown_tiles(const WorkItem* work, int n_work, const TileDev* tiles
 }
 
 // ------------------------------------------------------------------------------------------------
-// kernel 3: per destination pixel of one level
+// kernel 3 (generic): per destination pixel of one level (the coarsest level; classic path fall-back)
 //   lap  = sum over covering tiles (feed order) trunc16( sat16(G_l - pyrUp(G_{l+1})) * W_l )     [wraps like short +=]
 //   wsum = sum W_l                                                                                [float, feed order]
 //   v    = trunc16( lap / (wsum + 1e-5) )  ; v = sat16( pyrUp(C_{l+1}) + v )                      [collapse]

@@ -38,8 +38,6 @@ void launch_resize_exact(const uint8_t* src, int sw, int sh, int ch, long long s
 // number of valid (mask != 0) warped pixels of every image -> counts[img] (unsigned long long)
 void launch_count_valid(const ImageDev* imgs_dev, int n_img, const int* roi_w_host, const int* roi_h_host,
                         unsigned long long* counts_dev, cudaStream_t st);
-// fused warp: level 0 (G0 16S planar, W0 f32) of every tile in `work`
-void launch_warp_tiles(const WorkItem* work, int n_work, const TileDev* tiles, const ImageDev* imgs, cudaStream_t st);
 // G[l+1], W[l+1] = pyrDown(G[l], W[l]) for every tile block in `work`
 void launch_pyrdown_tiles(const WorkItem* work, int n_work, const TileDev* tiles, int level, cudaStream_t st);
 // accumulate (image order) + normalise + collapse one level of the destination; level 0 writes the output

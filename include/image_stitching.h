@@ -15,7 +15,8 @@
  *    `cameras[i].K().convertTo(K, CV_32F)` (image_stitching.cpp:1135-1136, 1150-1151).
  *  - Images are 8UC3 (or 8UC1 masks) interleaved HWC with a byte pitch; 16SC3 where OpenCV uses CV_16SC3.
  *  - Every data pointer may be a HOST pointer or a CUDA DEVICE pointer; the library detects which
- *    (cudaPointerGetAttributes).  Host data is staged through pinned buffers; device data is used in place.
+ *    (cudaPointerGetAttributes).  Host data is copied to device staging buffers (fastest from pinned memory);
+ *    device data is used in place.
  *  - Functions return ISB_OK (0) or a negative code whose value is the OpenCV error class the reference
  *    would have thrown (cv::Error::Code); isb_last_error() gives the message (thread-local).
  *    No exception crosses this boundary.  Handles are not thread-safe (same as the reference's objects).
