@@ -327,9 +327,10 @@ def run_ours(args, rank, world):
         # Same call, two composers in async_mode on two streams (a double-buffered serving loop, e.g. video-rate cfg4):
         # step k's upload overlaps step k-1's download on the full-duplex PCIe link.  Every step still uploads its
         # inputs from pinned host memory and downloads its panorama + mask.
-        streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+        depth = args.e2e_depth
+        streams = [torch.cuda.Stream(device=dev) for _ in range(depth)]
         slots = []
-        for _ in range(2):
+        for _ in range(depth):
             c2 = isb.Composer(rig.warp, rig.scale, rig.nb, cache_plan=True, async_mode=True)
             c2.plan(cams, sizes)
             slots.append((c2, torch.zeros((ph, pw, 3), dtype=torch.uint8).pin_memory(),
@@ -346,8 +347,8 @@ def run_ours(args, rank, world):
             for s_ in streams:
                 s_.wait_event(e0)
             for k in range(steps):
-                c2, ho, hm = slots[k % 2]
-                isb.set_stream(streams[k % 2].cuda_stream)
+                c2, ho, hm = slots[k % depth]
+                isb.set_stream(streams[k % depth].cuda_stream)
                 c2.run(np_imgs, np_gains, np_seams, out=ho.numpy(), out_mask=hm.numpy())
             for s_ in streams:
                 stream.wait_stream(s_)
@@ -356,14 +357,14 @@ def run_ours(args, rank, world):
             isb.set_stream(stream.cuda_stream)
             return e0.elapsed_time(e1)
 
-        pipelined(4)
+        pipelined(2 * depth)
         ms_e2e = pipelined(e2e_steps)
         # the async path must give the same panorama as the device-resident one
         comp.run(d_imgs, d_gains, d_seams, out=d_out, out_mask=d_mask)
         torch.cuda.synchronize()
-        e2e_extra.update({"pipeline_depth": 2,
+        e2e_extra.update({"pipeline_depth": depth,
                           "pipelined_equals_device_result": bool(torch.equal(slots[0][1], d_out.cpu()) and
-                                                                 torch.equal(slots[1][2], d_mask.cpu()))})
+                                                                 torch.equal(slots[-1][2], d_mask.cpu()))})
         del slots
     e2e_value = out_mp * e2e_steps / (ms_e2e / 1e3)
 
@@ -452,6 +453,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--video", type=int, default=0, help="also run N frames one call at a time and report p50/p95 latency")
     ap.add_argument("--no-e2e-pipeline", action="store_true", help="report the synchronous one-call-per-step e2e only")
+    ap.add_argument("--e2e-depth", type=int, default=3, help="composers in flight in the pipelined e2e measurement")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: final kernel stores into rank 0's panorama over NVLink peer memory (p2p) or NCCL send/recv")
     args = ap.parse_args()
