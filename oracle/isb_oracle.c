@@ -794,3 +794,100 @@ ORC_API void orc_compose(int kind, float scale, int n, const uint8_t* const* img
     orc_blender_destroy(b);
     free(corners);
 }
+
+/* ---- Blender::NO and FeatherBlender (image_stitching.cpp:1179, 1186-1191) ------------ */
+/* cv::detail::createWeightMap: distanceTransform(mask, DIST_L1, 3) * sharpness, truncated at 1.
+ * The 3x3 L1 chamfer is the exact city-block distance to the nearest zero pixel of the mask; with no zero pixel
+ * the non-IPP build yields 65534 (the IPP build FLT_MAX) - both clamp to 1 for any sharpness >= 1.6e-5. */
+ORC_API void orc_create_weight_map(const uint8_t* mask, int w, int h, float sharpness, float* weight)
+{
+    const int INF = 1 << 28;
+    int* d = (int*)malloc(sizeof(int) * (size_t)w * h);
+    for (size_t i = 0; i < (size_t)w * h; ++i) d[i] = mask[i] ? INF : 0;
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            int* p = d + (size_t)y * w + x;
+            if (x > 0 && p[-1] + 1 < *p) *p = p[-1] + 1;
+            if (y > 0 && p[-w] + 1 < *p) *p = p[-w] + 1;
+        }
+    for (int y = h - 1; y >= 0; --y)
+        for (int x = w - 1; x >= 0; --x) {
+            int* p = d + (size_t)y * w + x;
+            if (x < w - 1 && p[1] + 1 < *p) *p = p[1] + 1;
+            if (y < h - 1 && p[w] + 1 < *p) *p = p[w] + 1;
+        }
+    for (size_t i = 0; i < (size_t)w * h; ++i) {
+        float dist = d[i] >= INF ? 65534.f : (float)d[i];
+        float v = dist * sharpness;
+        weight[i] = v > 1.f ? 1.f : v;
+    }
+    free(d);
+}
+
+typedef struct {
+    int type; /* 0 = Blender::NO, 1 = FeatherBlender */
+    float sharpness;
+    int roi[4];
+    int16_t* dst;
+    uint8_t* dst_mask;
+    float* dst_weight;
+} orc_simple_blender;
+
+ORC_API orc_simple_blender* orc_simple_blender_create(int type, float sharpness)
+{
+    orc_simple_blender* b = (orc_simple_blender*)calloc(1, sizeof(orc_simple_blender));
+    b->type = type;
+    b->sharpness = sharpness;
+    return b;
+}
+ORC_API void orc_simple_blender_destroy(orc_simple_blender* b)
+{
+    if (!b) return;
+    free(b->dst); free(b->dst_mask); free(b->dst_weight); free(b);
+}
+ORC_API void orc_simple_blender_prepare(orc_simple_blender* b, const int* roi)
+{
+    free(b->dst); free(b->dst_mask); free(b->dst_weight);
+    memcpy(b->roi, roi, 4 * sizeof(int));
+    size_t n = (size_t)roi[2] * roi[3];
+    b->dst = (int16_t*)calloc(n * 3, sizeof(int16_t));
+    b->dst_mask = (uint8_t*)calloc(n, 1);
+    b->dst_weight = (float*)calloc(n, sizeof(float));
+}
+ORC_API void orc_simple_blender_feed(orc_simple_blender* b, const int16_t* img, const uint8_t* mask, int w, int h, int tlx, int tly)
+{
+    int dx = tlx - b->roi[0], dy = tly - b->roi[1], dw = b->roi[2];
+    if (b->type == 0) { /* Blender::feed */
+        for (int y = 0; y < h; ++y)
+            for (int x = 0; x < w; ++x) {
+                size_t s = (size_t)y * w + x, d = (size_t)(dy + y) * dw + dx + x;
+                if (mask[s])
+                    for (int c = 0; c < 3; ++c) b->dst[d * 3 + c] = img[s * 3 + c];
+                b->dst_mask[d] |= mask[s];
+            }
+        return;
+    }
+    float* wm = (float*)malloc(sizeof(float) * (size_t)w * h);
+    orc_create_weight_map(mask, w, h, b->sharpness, wm);
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            size_t s = (size_t)y * w + x, d = (size_t)(dy + y) * dw + dx + x;
+            for (int c = 0; c < 3; ++c)
+                b->dst[d * 3 + c] = (int16_t)(b->dst[d * 3 + c] + (int16_t)(int)((float)img[s * 3 + c] * wm[s]));
+            b->dst_weight[d] = b->dst_weight[d] + wm[s];
+        }
+    free(wm);
+}
+ORC_API void orc_simple_blender_blend(orc_simple_blender* b, int16_t* dst, uint8_t* dst_mask)
+{
+    size_t n = (size_t)b->roi[2] * b->roi[3];
+    for (size_t i = 0; i < n; ++i) {
+        if (b->type == 1) {
+            float den = b->dst_weight[i] + 1e-5f;
+            for (int c = 0; c < 3; ++c) b->dst[i * 3 + c] = (int16_t)(int)((float)b->dst[i * 3 + c] / den);
+            b->dst_mask[i] = b->dst_weight[i] > 1e-5f ? 255 : 0;
+        }
+        dst_mask[i] = b->dst_mask[i];
+        for (int c = 0; c < 3; ++c) dst[i * 3 + c] = b->dst_mask[i] ? b->dst[i * 3 + c] : 0;
+    }
+}

@@ -26,6 +26,8 @@ def lib():
     if _LIB is None:
         _LIB = C.CDLL(build())
         _LIB.orc_blender_create.restype = C.c_void_p
+        _LIB.orc_simple_blender_create.restype = C.c_void_p
+        _LIB.orc_simple_blender_create.argtypes = [C.c_int, C.c_float]
         _LIB.orc_blender_num_bands.restype = C.c_int
     return _LIB
 
@@ -216,6 +218,43 @@ class Blender:
         dst = np.empty((rf[3], rf[2], 3), np.int16)
         m = np.empty((rf[3], rf[2]), np.uint8)
         lib().orc_blender_blend(self._h, _p(dst), _p(m))
+        return dst, m
+
+
+def create_weight_map(mask, sharpness):
+    mask = np.ascontiguousarray(mask, np.uint8)
+    o = np.empty(mask.shape, np.float32)
+    lib().orc_create_weight_map(_p(mask), mask.shape[1], mask.shape[0], C.c_float(sharpness), _p(o))
+    return o
+
+
+class SimpleBlender:
+    """Blender::NO (type 0) and FeatherBlender (type 1) restatements with the cv2 call surface."""
+
+    def __init__(self, btype, sharpness=0.02):
+        self._h = C.c_void_p(lib().orc_simple_blender_create(int(btype), float(sharpness)))
+
+    def __del__(self):
+        try:
+            lib().orc_simple_blender_destroy(self._h)
+        except Exception:
+            pass
+
+    def prepare(self, roi):
+        self.roi = tuple(int(v) for v in roi)
+        r = np.ascontiguousarray(roi, np.int32)
+        lib().orc_simple_blender_prepare(self._h, _p(r))
+
+    def feed(self, img16, mask, tl):
+        img16 = np.ascontiguousarray(img16, np.int16)
+        mask = np.ascontiguousarray(mask, np.uint8)
+        h, w = mask.shape
+        lib().orc_simple_blender_feed(self._h, _p(img16), _p(mask), w, h, int(tl[0]), int(tl[1]))
+
+    def blend(self):
+        dst = np.empty((self.roi[3], self.roi[2], 3), np.int16)
+        m = np.empty((self.roi[3], self.roi[2]), np.uint8)
+        lib().orc_simple_blender_blend(self._h, _p(dst), _p(m))
         return dst, m
 
 
