@@ -147,3 +147,32 @@ def test_ingest_presteps(cv2_parity):
     for (dw, dh) in [(194, 135), (531, 371), (1000, 37), (53, 700)]:
         ref = cv2.resize(img, (dw, dh), interpolation=cv2.INTER_LINEAR_EXACT)
         assert np.array_equal(ref, orc.resize_linear_exact_ex(img, dw, dh))
+
+
+def test_feather_and_no_blender(cv2_parity):
+    """Blender::NO and FeatherBlender incl. createWeightMap (image_stitching.cpp:1175-1191, SURVEY.md 8f rank 3)."""
+    cv2 = cv2_parity
+    rng = np.random.default_rng(0)
+    corners = [(0, 0), (150, -30), (-77, 41)]
+    sizes = [(300, 200), (257, 213), (190, 260)]
+    roi = cv2.detail.resultRoi(corners=corners, sizes=sizes)
+    full = np.full((50, 60), 255, np.uint8)  # no zero pixel: the distance saturates, the weight clamps to 1
+    assert np.array_equal(cv2.detail.createWeightMap(full, 0.02, None), orc.create_weight_map(full, 0.02))
+    for btype, sharp in [(0, 0.02), (1, 0.02), (1, 0.1), (1, 1 / 37.3)]:
+        b = cv2.detail.Blender_createDefault(cv2.detail.Blender_NO) if btype == 0 else cv2.detail_FeatherBlender(sharp)
+        b.prepare(roi)
+        b2 = orc.SimpleBlender(btype, sharp)
+        b2.prepare(roi)
+        for (cx, cy), (sw, sh) in zip(corners, sizes):
+            img = rng.integers(0, 256, (sh, sw, 3)).astype(np.int16)
+            m = np.zeros((sh, sw), np.uint8)
+            m[10:-10, 10:-10] = 255
+            m[20:40, 20:60] = rng.integers(0, 256, (20, 40))
+            m[50:60, 50:90] = 0
+            if btype == 1:
+                assert np.array_equal(cv2.detail.createWeightMap(m, sharp, None), orc.create_weight_map(m, sharp))
+            b.feed(img, m, (cx, cy))
+            b2.feed(img, m, (cx, cy))
+        r, rm = b.blend(None, None)
+        r2, rm2 = b2.blend()
+        assert np.array_equal(r, r2) and np.array_equal(rm, rm2), (btype, sharp)
