@@ -43,6 +43,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     common = ["-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a", "-fmad=false",
               "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-fvisibility=hidden,-Wall", "-I",
               os.path.join(HERE, "..", "include")]
+    common += os.environ.get("ISB_NVCC_FLAGS", "").split()  # tuning experiments (-DISB_...), empty in production
     if verbose:
         common += ["-Xptxas", "-v"]
     objs = []

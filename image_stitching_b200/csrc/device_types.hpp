@@ -16,6 +16,7 @@ struct ImageDev {
     const uint8_t* src;   // 8UC3 interleaved (or 8UC1 for mask warps)
     long long spitch;     // bytes
     unsigned sbytes;      // spitch * sh when the vectorised sampler may be used (8-B aligned base, < 4 GB), else 0
+    int fast_h;           // rows y0 in [0, fast_h) whose two 16-byte tap windows stay inside the buffer for every x0 <= sw - 2
     int sw, sh;           // source size
     int roi_w, roi_h;     // warped size (warpRoi)
     float kr[9];          // k_rinv = K * R^T

@@ -911,6 +911,9 @@ void Composer::run(const isb_image* imgs, const isb_gainmap* gains, const isb_ma
         {   // the vectorised sampler reads aligned 16-byte windows: needs an 8-B aligned base and 32-bit offsets
             const unsigned long long extent = (unsigned long long)I.spitch * (I.sh - 1) + (unsigned long long)I.sw * 3;
             I.sbytes = ((reinterpret_cast<uintptr_t>(I.src) & 7) == 0 && extent < 0xFFFFFF00ull) ? (unsigned)extent : 0u;
+            // window of tap row y0 + 1 at x0 = sw - 2 ends at (y0 + 1) * pitch + 3 * (sw - 2) + 16 at most
+            const long long room = (long long)I.sbytes - 16 - 3ll * (I.sw - 2);
+            I.fast_h = (I.sbytes && I.sw >= 2 && room >= I.spitch) ? (int)std::min<long long>(room / I.spitch, I.sh - 1) : 0;
         }
         if (gains && gains[i].data) {
             const isb_gainmap& g = gains[i];

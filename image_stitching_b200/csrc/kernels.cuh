@@ -69,7 +69,10 @@ constexpr int kFastDownRowsSmall = 4;  // ... at the coarser levels, where paral
 constexpr int kFastDownWarps = 8;   // warps per CTA, stacked in y  -> CTA block = 64 x 128 outputs
 
 // geometry of the CTA blocks the planner must use when it builds work lists
-constexpr int kWarpBlockW = 64, kWarpBlockH = 32;
+#ifndef ISB_WARP_BLOCK_H
+#define ISB_WARP_BLOCK_H 128
+#endif
+constexpr int kWarpBlockW = 64, kWarpBlockH = ISB_WARP_BLOCK_H;
 constexpr int kDownBlockW = 32, kDownBlockH = 8;  // in OUTPUT (level l+1) pixels
 
 }  // namespace isb
