@@ -20,6 +20,8 @@ struct ImageDev {
     int sw, sh;           // source size
     int roi_w, roi_h;     // warped size (warpRoi)
     float kr[9];          // k_rinv = K * R^T
+    float zlo;            // the fused warp divides by z with a shared reciprocal when z > zlo (2^-40, or +inf when the
+                          // operands are not provably below 2^40: then every pixel takes the IEEE division path)
     const F2* col;        // [roi_w] (sin u', cos u')
     const F2* row;        // [roi_h] (sin(pi - v'), cos(pi - v')) | (1, v')
     const float* gain;    // gain grid gh x gw (nullptr: no gain)

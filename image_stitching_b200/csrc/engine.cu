@@ -899,6 +899,22 @@ void Composer::run(const isb_image* imgs, const isb_gainmap* gains, const isb_ma
         std::memcpy(I.kr, P.proj.k_rinv, sizeof(I.kr));
         I.col = reinterpret_cast<const F2*>(tb + P.col_off);
         I.row = reinterpret_cast<const F2*>(tb + P.row_off);
+        {   // |x|, |y|, |z| of the inverse map are at most 3 * max|kr| * max(1, |y_|): the shared-reciprocal division of
+            // the fused warp is exact while they stay below 2^40 (and z above 2^-40)
+            if (P.row_bmax < 0.f) {
+                float m = 0.f;
+                for (const Float2& r : P.row) m = std::fabs(r.b) <= m ? m : std::fabs(r.b);  // NaN propagates
+                P.row_bmax = m;
+            }
+            float kmax = 0.f;
+            bool finite = std::isfinite(P.row_bmax);
+            for (float k : I.kr) {
+                finite = finite && std::isfinite(k);
+                kmax = std::max(kmax, std::fabs(k));
+            }
+            const double bound = 3.0 * (double)kmax * std::max(1.0, (double)P.row_bmax);
+            I.zlo = (finite && bound < 0x1p40) ? 0x1p-40f : INFINITY;
+        }
         if (mem_kind(im.data) == MemKind::Device) {
             I.src = im.data;
             I.spitch = (long long)im.pitch;

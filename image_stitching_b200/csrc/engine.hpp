@@ -70,6 +70,7 @@ struct ImagePlan {
     // offsets into the composer's table arena
     size_t col_off = 0, row_off = 0, gx_off = 0, gy_off = 0, mx_off = 0, my_off = 0;
     int gain_w = -1, gain_h = -1, seam_w = -1, seam_h = -1;  // sizes the cached coefficient tables were built for
+    float row_bmax = -1.f;  // max |row[j].b| (bounds the inverse-map operands), computed on first use
 };
 
 // The pyramid engine: owns the per-tile pyramids and the destination pyramid, runs kernels 2 and 3.
