@@ -90,8 +90,14 @@ def lib():
     L.isb_launch_count.restype = C.c_longlong
     L.isb_composer_stage_name.restype = C.c_char_p
     L.isb_warper_get_scale.restype = C.c_float
-    for f in ("isb_warper_create", "isb_compensator_create", "isb_blender_create", "isb_composer_create"):
+    for f in ("isb_warper_create", "isb_compensator_create", "isb_blender_create", "isb_composer_create",
+              "isb_simple_blender_create"):
         getattr(L, f).restype = C.c_void_p
+    L.isb_simple_blender_create.argtypes = [C.c_int, C.c_float]
+    L.isb_simple_blender_set_sharpness.argtypes = [C.c_void_p, C.c_float]
+    L.isb_simple_blender_sharpness.argtypes = [C.c_void_p]
+    L.isb_simple_blender_sharpness.restype = C.c_float
+    L.isb_create_weight_map.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_size_t]
     L.isb_warper_create.argtypes = [C.c_int, C.c_float]
     L.isb_warper_set_scale.argtypes = [C.c_void_p, C.c_float]
     L.isb_num_bands_for.argtypes = [C.c_int, C.c_int, C.c_float]
@@ -99,7 +105,8 @@ def lib():
                                           C.c_size_t, C.c_double, C.c_double]
     L.isb_quat_slerp.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
     L.isb_quat_from_axis_angle.argtypes = [C.c_void_p, C.c_double, C.c_void_p]
-    for f in ("isb_warper_destroy", "isb_compensator_destroy", "isb_blender_destroy", "isb_composer_destroy"):
+    for f in ("isb_warper_destroy", "isb_compensator_destroy", "isb_blender_destroy", "isb_composer_destroy",
+              "isb_simple_blender_destroy"):
         getattr(L, f).argtypes = [C.c_void_p]
         getattr(L, f).restype = None
     _lib = L
@@ -524,6 +531,85 @@ class MultiBandBlender:
         _chk(lib().isb_blender_blend(self._h, out.ctypes.data_as(C.c_void_p), C.c_size_t(rf[2] * 6),
                                      m.ctypes.data_as(C.c_void_p), C.c_size_t(rf[2])))
         return out, m
+
+
+BLENDER_NO, BLENDER_FEATHER, BLENDER_MULTI_BAND = 0, 1, 2  # cv::detail::Blender::{NO, FEATHER, MULTI_BAND}
+
+
+def createWeightMap(mask, sharpness):
+    """cv2.detail.createWeightMap(mask, sharpness, None): min(1, sharpness * L1 distance to the nearest zero pixel)."""
+    mask = np.ascontiguousarray(mask, np.uint8)
+    h, w = mask.shape
+    out = np.empty((h, w), np.float32)
+    _chk(lib().isb_create_weight_map(mask.ctypes.data_as(C.c_void_p), w, w, h, float(sharpness),
+                                     out.ctypes.data_as(C.c_void_p), w * 4))
+    return out
+
+
+class _SimpleBlender:
+    """cv2.detail.Blender_createDefault(Blender_NO) / cv2.detail_FeatherBlender (image_stitching.cpp:1175-1191)."""
+
+    def __init__(self, btype, sharpness):
+        h = lib().isb_simple_blender_create(int(btype), float(sharpness))
+        if not h:
+            raise IsbError(-5, lib().isb_last_error().decode())
+        self._h = C.c_void_p(h)
+        self._roi = None
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().isb_simple_blender_destroy(self._h)
+            self._h = None
+
+    def prepare(self, *args):
+        if len(args) == 1:
+            self._roi = tuple(int(v) for v in args[0])
+        else:
+            self._roi = tuple(resultRoi(args[0], args[1]))
+        _chk(lib().isb_simple_blender_prepare_roi(self._h, (C.c_int * 4)(*self._roi)))
+
+    def feed(self, img, mask, tl):
+        if not _is_torch(img) and np.asarray(img).dtype != np.int16:
+            raise IsbError(-215, "Assertion failed: img.type() == CV_16SC3")
+        if not _is_torch(mask) and np.asarray(mask).dtype != np.uint8:
+            raise IsbError(-215, "Assertion failed: mask.type() == CV_8U")
+        ip, _i = _ptr(img)
+        mp, _m = _ptr(mask)
+        h, w = _shape(mask)[:2]
+        _chk(lib().isb_simple_blender_feed(self._h, C.c_void_p(ip), C.c_size_t(w * 6), C.c_void_p(mp), C.c_size_t(w), w, h,
+                                           int(tl[0]), int(tl[1])))
+
+    def blend(self, dst=None, dst_mask=None):
+        if self._roi is None:
+            raise IsbError(-215, "Assertion failed: prepare() must be called before blend()")
+        w, h = self._roi[2], self._roi[3]
+        out = np.empty((h, w, 3), np.int16)
+        m = np.empty((h, w), np.uint8)
+        _chk(lib().isb_simple_blender_blend(self._h, out.ctypes.data_as(C.c_void_p), C.c_size_t(w * 6),
+                                            m.ctypes.data_as(C.c_void_p), C.c_size_t(w)))
+        return out, m
+
+
+class FeatherBlender(_SimpleBlender):
+    def __init__(self, sharpness=0.02):
+        super().__init__(BLENDER_FEATHER, sharpness)
+
+    def setSharpness(self, val):
+        _chk(lib().isb_simple_blender_set_sharpness(self._h, float(val)))
+
+    def sharpness(self):
+        return float(lib().isb_simple_blender_sharpness(self._h))
+
+
+def Blender_createDefault(btype, try_gpu=False):
+    """cv2.detail.Blender_createDefault: NO -> plain Blender, FEATHER -> FeatherBlender(), MULTI_BAND -> MultiBandBlender()."""
+    if btype == BLENDER_NO:
+        return _SimpleBlender(BLENDER_NO, 0.02)
+    if btype == BLENDER_FEATHER:
+        return FeatherBlender()
+    if btype == BLENDER_MULTI_BAND:
+        return MultiBandBlender()
+    raise IsbError(-5, "unknown blender type")
 
 
 # ---------------------------------------------------------------------------------------------------

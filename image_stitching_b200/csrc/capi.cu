@@ -14,6 +14,7 @@ using namespace isb;
 struct isb_warper { Warper impl; isb_warper(int k, float s) : impl(k, s) {} };
 struct isb_compensator { Compensator impl; isb_compensator(int w, int h) : impl(w, h) {} };
 struct isb_blender { Blender impl; explicit isb_blender(int nb) : impl(nb) {} };
+struct isb_simple_blender { SimpleBlender impl; isb_simple_blender(int t, float s) : impl(t, s) {} };
 struct isb_composer { Composer impl; explicit isb_composer(const isb_config& c) : impl(c) {} };
 
 static thread_local std::string t_error;
@@ -350,6 +351,47 @@ int isb_blender_feed(isb_blender* b, const int16_t* img, size_t ipitch, const ui
 int isb_blender_blend(isb_blender* b, int16_t* dst, size_t dpitch, uint8_t* dmask, size_t mpitch)
 {
     return guarded([&] { NOT_NULL(b); b->impl.blend(dst, dpitch, dmask, mpitch); });
+}
+
+// ---- Blender::NO / FeatherBlender -------------------------------------------------------------------
+isb_simple_blender* isb_simple_blender_create(int type, float sharpness)
+{
+    if (type != ISB_BLENDER_NO && type != ISB_BLENDER_FEATHER) {
+        t_error = "isb_simple_blender_create: type must be ISB_BLENDER_NO or ISB_BLENDER_FEATHER";
+        return nullptr;
+    }
+    return new (std::nothrow) isb_simple_blender(type, sharpness);
+}
+void isb_simple_blender_destroy(isb_simple_blender* b) { delete b; }
+int isb_simple_blender_set_sharpness(isb_simple_blender* b, float sharpness)
+{
+    return guarded([&] { NOT_NULL(b); b->impl.set_sharpness(sharpness); });
+}
+float isb_simple_blender_sharpness(const isb_simple_blender* b) { return b ? b->impl.sharpness() : -1.f; }
+int isb_simple_blender_prepare(isb_simple_blender* b, const int* corners, const int* sizes, int n)
+{
+    return guarded([&] {
+        NOT_NULL(b); NOT_NULL(corners); NOT_NULL(sizes);
+        ISB_ASSERT(n > 0);
+        b->impl.prepare(result_roi(corners, sizes, n));
+    });
+}
+int isb_simple_blender_prepare_roi(isb_simple_blender* b, const int rect[4])
+{
+    return guarded([&] { NOT_NULL(b); NOT_NULL(rect); b->impl.prepare(Rect{rect[0], rect[1], rect[2], rect[3]}); });
+}
+int isb_simple_blender_feed(isb_simple_blender* b, const int16_t* img, size_t ipitch, const uint8_t* mask, size_t mpitch, int w,
+                            int h, int tlx, int tly)
+{
+    return guarded([&] { NOT_NULL(b); b->impl.feed(img, ipitch, mask, mpitch, w, h, tlx, tly); });
+}
+int isb_simple_blender_blend(isb_simple_blender* b, int16_t* dst, size_t dpitch, uint8_t* dmask, size_t mpitch)
+{
+    return guarded([&] { NOT_NULL(b); b->impl.blend(dst, dpitch, dmask, mpitch); });
+}
+int isb_create_weight_map(const uint8_t* mask, size_t mpitch, int w, int h, float sharpness, float* weight, size_t wpitch)
+{
+    return guarded([&] { SimpleBlender::weight_map(mask, mpitch, w, h, sharpness, weight, wpitch); });
 }
 
 // ---- composer ---------------------------------------------------------------------------------------

@@ -90,8 +90,7 @@ void* DevBuf::ensure(size_t bytes)
 }
 
 // copy a (rows x row_bytes) block between any two memory kinds on `st`
-static void copy2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t row_bytes, size_t rows,
-                   cudaStream_t st)
+void copy2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t row_bytes, size_t rows, cudaStream_t st)
 {
     if (rows == 0 || row_bytes == 0) return;
     if (dpitch == row_bytes && spitch == row_bytes)

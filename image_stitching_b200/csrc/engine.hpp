@@ -32,6 +32,8 @@ void require_device();  // throws ISB_ERR_GPU_API when no CUDA device is usable 
 
 enum class MemKind { Host, HostPinned, Device };
 MemKind mem_kind(const void* p);
+// copy a (rows x row_bytes) block between any two memory kinds on `st`
+void copy2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t row_bytes, size_t rows, cudaStream_t st);
 
 // growable device allocation (never shrinks; reused across calls)
 class DevBuf {
@@ -180,6 +182,28 @@ private:
     bool prepared_ = false;
     PyramidEngine eng_;
     DevBuf img_, mask_, out16_, outm_;
+};
+
+// cv::detail::Blender (type NO) and cv::detail::FeatherBlender (image_stitching.cpp:1175-1191): destination-resident
+// 16SC3 image, 8U mask and (feather) f32 weight sum; kernels in simple_blend.cu.
+class SimpleBlender {
+public:
+    SimpleBlender(int type, float sharpness) : type_(type), sharpness_(sharpness) {}
+    int type() const { return type_; }
+    float sharpness() const { return sharpness_; }
+    void set_sharpness(float s) { sharpness_ = s; }
+    const Rect& roi() const { return roi_; }
+    void prepare(const Rect& roi);
+    void feed(const int16_t* img, size_t ipitch, const uint8_t* mask, size_t mpitch, int w, int h, int tlx, int tly);
+    void blend(int16_t* dst, size_t dpitch, uint8_t* dmask, size_t mpitch);
+    // cv::detail::createWeightMap(mask, sharpness, weight) on its own
+    static void weight_map(const uint8_t* mask, size_t mpitch, int w, int h, float sharpness, float* weight, size_t wpitch);
+private:
+    int type_;
+    float sharpness_;
+    bool prepared_ = false;
+    Rect roi_{};
+    DevBuf dst_, dmask_, dweight_, img_, mask_, wmap_, dist_;
 };
 
 class Composer {

@@ -203,6 +203,28 @@ ISB_API int isb_blender_feed(isb_blender* b, const int16_t* img, size_t img_pitc
 ISB_API int isb_blender_blend(isb_blender* b, int16_t* dst, size_t dst_pitch, uint8_t* dst_mask, size_t mask_pitch);
 
 /* ============================================================================================
+ * cv::detail::Blender (Blender::NO) and cv::detail::FeatherBlender  (image_stitching.cpp:1175-1191:
+ * Blender::createDefault(blend_type), the blend_width < 1 fall-back to Blender::NO, FeatherBlender::setSharpness)
+ * ============================================================================================ */
+enum { ISB_BLENDER_NO = 0, ISB_BLENDER_FEATHER = 1, ISB_BLENDER_MULTI_BAND = 2 }; /* == cv::detail::Blender::{NO,FEATHER,MULTI_BAND} */
+typedef struct isb_simple_blender isb_simple_blender;
+/* Blender::createDefault(type) for type NO / FEATHER (MULTI_BAND is isb_blender above); sharpness as FeatherBlender(0.02f) */
+ISB_API isb_simple_blender* isb_simple_blender_create(int type, float sharpness);
+ISB_API void isb_simple_blender_destroy(isb_simple_blender* b);
+ISB_API int isb_simple_blender_set_sharpness(isb_simple_blender* b, float sharpness); /* fb->setSharpness(1.f / blend_width) */
+ISB_API float isb_simple_blender_sharpness(const isb_simple_blender* b);
+ISB_API int isb_simple_blender_prepare(isb_simple_blender* b, const int* corners_xy, const int* sizes_wh, int n);
+ISB_API int isb_simple_blender_prepare_roi(isb_simple_blender* b, const int rect_xywh[4]);
+/* feed(img CV_16SC3, mask CV_8U, tl); the image rect must lie inside the prepared ROI (CV_Assert in the reference) */
+ISB_API int isb_simple_blender_feed(isb_simple_blender* b, const int16_t* img, size_t img_pitch, const uint8_t* mask,
+                                    size_t mask_pitch, int w, int h, int tl_x, int tl_y);
+/* blend(dst CV_16SC3, dst_mask CV_8U) of the prepared ROI size.  Single use per prepare(). */
+ISB_API int isb_simple_blender_blend(isb_simple_blender* b, int16_t* dst, size_t dst_pitch, uint8_t* dst_mask, size_t mask_pitch);
+/* cv::detail::createWeightMap(mask, sharpness, weight): weight = min(1, sharpness * distanceTransform(mask, DIST_L1, 3)) */
+ISB_API int isb_create_weight_map(const uint8_t* mask, size_t mask_pitch, int w, int h, float sharpness, float* weight,
+                                  size_t weight_pitch);
+
+/* ============================================================================================
  * Fused path: the whole loop image_stitching.cpp:1086-1229 (warp, mask, gain, ->16S, seam mask,
  * prepare, feed x n, blend, saturate to 8U) without materialising xmap/ymap or the intermediates.
  * ============================================================================================ */

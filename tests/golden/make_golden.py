@@ -67,6 +67,42 @@ def main():
     prim["gain_up"] = cv2.resize(g, (451, 353), interpolation=cv2.INTER_LINEAR)
     np.savez_compressed(os.path.join(OUT, "primitives.npz"), **prim)
     print("primitives written")
+    simple_blenders()
+
+
+def simple_blend_inputs():
+    """Seeded inputs of the Blender::NO / FeatherBlender vectors (shared with the tests)."""
+    rng = np.random.default_rng(77)
+    corners = [(0, 0), (150, -30), (-77, 41)]
+    sizes = [(300, 200), (257, 213), (190, 260)]
+    imgs, masks = [], []
+    for (sw, sh) in sizes:
+        imgs.append(rng.integers(0, 256, (sh, sw, 3)).astype(np.int16))
+        m = np.zeros((sh, sw), np.uint8)
+        m[10:-10, 10:-10] = 255
+        m[20:40, 20:60] = rng.integers(0, 256, (20, 40))  # grey values count as "inside" for the distance transform
+        m[50:60, 50:90] = 0
+        masks.append(m)
+    return corners, sizes, imgs, masks
+
+
+def simple_blenders():
+    """Blender::NO and FeatherBlender (image_stitching.cpp:1175-1191) + createWeightMap."""
+    cvr.set_parity_mode(True)
+    corners, sizes, imgs, masks = simple_blend_inputs()
+    roi = cv2.detail.resultRoi(corners=corners, sizes=sizes)
+    out = {"roi": np.array(roi, np.int32)}
+    for tag, btype, sharp in [("no", 0, 0.02), ("feather", 1, 0.02), ("feather_sharp", 1, 1 / 37.3)]:
+        b = cv2.detail.Blender_createDefault(cv2.detail.Blender_NO) if btype == 0 else cv2.detail_FeatherBlender(sharp)
+        b.prepare(roi)
+        for img, m, c in zip(imgs, masks, corners):
+            b.feed(img, m, c)
+        r, rm = b.blend(None, None)
+        out[tag + "_result16"], out[tag + "_mask"] = r, rm
+    out["wm0"] = cv2.detail.createWeightMap(masks[0], 0.02, None)
+    out["wm_full"] = cv2.detail.createWeightMap(np.full((40, 50), 255, np.uint8), 0.02, None)
+    np.savez_compressed(os.path.join(OUT, "simple_blend.npz"), **out)
+    print("simple blenders written")
 
 
 if __name__ == "__main__":

@@ -344,3 +344,77 @@ def test_seam_scale_auxiliary_warp():
         c1, a = w.warp(m, Ks, R, isb.INTER_NEAREST, isb.BORDER_CONSTANT)
         c2, b = orc.warp(rig.warp, ss, m, Ks, R, orc.NEAREST, 0)
         assert c1 == c2 and np.array_equal(a, b)
+
+
+# ---- Blender::NO and FeatherBlender (image_stitching.cpp:1175-1191) ---------------------
+def test_create_weight_map_bit_exact():
+    rng = np.random.default_rng(21)
+    g = np.load(os.path.join(GOLD, "simple_blend.npz"))
+    from test_oracle_golden import simple_blend_inputs
+    _, _, _, masks = simple_blend_inputs()
+    assert np.array_equal(isb.createWeightMap(masks[0], 0.02), g["wm0"])
+    assert np.array_equal(isb.createWeightMap(np.full((40, 50), 255, np.uint8), 0.02), g["wm_full"])  # no zero pixel
+    for (h, w) in [(1, 1), (1, 77), (91, 1), (33, 47), (200, 333), (64, 1025)]:
+        m = (rng.random((h, w)) > 0.02).astype(np.uint8) * rng.integers(1, 256, (h, w)).astype(np.uint8)
+        for sharp in (0.02, 0.5, 1 / 390.0):
+            assert np.array_equal(isb.createWeightMap(m, sharp), orc.create_weight_map(m, sharp)), (h, w, sharp)
+    with pytest.raises(isb.IsbError):  # the saturated "no zero pixel" distance must still clamp to 1
+        isb.createWeightMap(np.full((4, 4), 255, np.uint8), 1e-6)
+
+
+@pytest.mark.parametrize("tag,btype,sharp", [("no", 0, 0.02), ("feather", 1, 0.02), ("feather_sharp", 1, 1 / 37.3)])
+def test_simple_blenders_bit_exact(tag, btype, sharp):
+    from test_oracle_golden import simple_blend_inputs
+    g = np.load(os.path.join(GOLD, "simple_blend.npz"))
+    corners, sizes, imgs, masks = simple_blend_inputs()
+    b = isb.Blender_createDefault(btype)
+    if btype == isb.BLENDER_FEATHER:
+        assert abs(b.sharpness() - 0.02) < 1e-9  # FeatherBlender(0.02f) default
+        b.setSharpness(sharp)
+    b.prepare(corners, sizes)
+    for img, m, c in zip(imgs, masks, corners):
+        b.feed(img, m, c)
+    r, rm = b.blend()
+    assert np.array_equal(rm, g[tag + "_mask"])
+    assert np.array_equal(r, g[tag + "_result16"])
+    with pytest.raises(isb.IsbError):  # single use per prepare()
+        b.blend()
+
+
+def test_simple_blenders_vs_oracle_wraparound_and_contract():
+    """int16 wrap-around of the feather accumulator, negative inputs, device-resident inputs, ROI assertion."""
+    rng = np.random.default_rng(5)
+    roi = (-20, -10, 400, 300)
+    for btype in (isb.BLENDER_NO, isb.BLENDER_FEATHER):
+        a = isb.Blender_createDefault(btype)
+        o = orc.SimpleBlender(btype, 0.02)
+        a.prepare(roi)
+        o.prepare(roi)
+        for k in range(6):  # six overlapping full-weight images of large values wrap the int16 sum
+            w, h = 300, 250
+            img = rng.integers(-30000, 30000, (h, w, 3)).astype(np.int16)
+            m = np.full((h, w), 255, np.uint8)
+            m[:, :3] = 0
+            tl = (-20 + 7 * k, -10 + 5 * k)
+            a.feed(img, m, tl)
+            o.feed(img, m, tl)
+        r1, m1 = a.blend()
+        r2, m2 = o.blend()
+        assert np.array_equal(m1, m2) and np.array_equal(r1, r2), btype
+    b = isb.FeatherBlender()
+    with pytest.raises(isb.IsbError):  # feed before prepare
+        b.feed(np.zeros((8, 8, 3), np.int16), np.zeros((8, 8), np.uint8), (0, 0))
+    b.prepare((0, 0, 32, 32))
+    with pytest.raises(isb.IsbError):  # image outside dst_roi_
+        b.feed(np.zeros((8, 8, 3), np.int16), np.zeros((8, 8), np.uint8), (30, 0))
+    torch = pytest.importorskip("torch")
+    img = rng.integers(0, 256, (16, 16, 3)).astype(np.int16)
+    m = np.full((16, 16), 255, np.uint8)
+    m[0, :] = 0
+    b.feed(torch.from_numpy(img).cuda(), torch.from_numpy(m).cuda(), (4, 4))  # device pointers are used in place
+    o = orc.SimpleBlender(1, 0.02)
+    o.prepare((0, 0, 32, 32))
+    o.feed(img, m, (4, 4))
+    r1, m1 = b.blend()
+    r2, m2 = o.blend()
+    assert np.array_equal(m1, m2) and np.array_equal(r1, r2)

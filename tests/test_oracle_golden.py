@@ -57,3 +57,35 @@ def test_primitives():
     # the float gain-map upsample is the one step that is only pinned to <= 1 ulp
     assert np.max(np.abs(gu.view(np.int32).astype(np.int64) - p["gain_up"].view(np.int32))) <= 1
     assert np.mean(gu != p["gain_up"]) < 0.02
+
+
+def simple_blend_inputs():
+    """The seeded inputs tests/golden/make_golden.py::simple_blend_inputs used (kept in step with it)."""
+    rng = np.random.default_rng(77)
+    corners = [(0, 0), (150, -30), (-77, 41)]
+    sizes = [(300, 200), (257, 213), (190, 260)]
+    imgs, masks = [], []
+    for (sw, sh) in sizes:
+        imgs.append(rng.integers(0, 256, (sh, sw, 3)).astype(np.int16))
+        m = np.zeros((sh, sw), np.uint8)
+        m[10:-10, 10:-10] = 255
+        m[20:40, 20:60] = rng.integers(0, 256, (20, 40))
+        m[50:60, 50:90] = 0
+        masks.append(m)
+    return corners, sizes, imgs, masks
+
+
+def test_simple_blenders_match_golden():
+    """Blender::NO / FeatherBlender / createWeightMap restatements against cv2-generated vectors."""
+    g = np.load(os.path.join(GOLD, "simple_blend.npz"))
+    corners, sizes, imgs, masks = simple_blend_inputs()
+    assert orc.result_roi(corners, sizes) == tuple(g["roi"])
+    assert np.array_equal(orc.create_weight_map(masks[0], 0.02), g["wm0"])
+    assert np.array_equal(orc.create_weight_map(np.full((40, 50), 255, np.uint8), 0.02), g["wm_full"])
+    for tag, btype, sharp in [("no", 0, 0.02), ("feather", 1, 0.02), ("feather_sharp", 1, 1 / 37.3)]:
+        b = orc.SimpleBlender(btype, sharp)
+        b.prepare(tuple(g["roi"]))
+        for img, m, c in zip(imgs, masks, corners):
+            b.feed(img, m, c)
+        r, rm = b.blend()
+        assert np.array_equal(r, g[tag + "_result16"]) and np.array_equal(rm, g[tag + "_mask"]), tag
