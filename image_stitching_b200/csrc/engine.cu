@@ -133,7 +133,8 @@ int PyramidEngine::add_tile(int img_index, int w, int h, int tlx, int tly)
     return add_rect(img_index, tl[0] - g_.roi.x, tl[1] - g_.roi.y, br[0] - tl[0], br[1] - tl[1], tlx, tly, w, h);
 }
 
-int PyramidEngine::add_rect(int img_index, int X0, int Y0, int W, int H, int tlx, int tly, int roi_w, int roi_h)
+int PyramidEngine::add_rect(int img_index, int X0, int Y0, int W, int H, int tlx, int tly, int roi_w, int roi_h,
+                            const uint8_t* need_grid, int grid_X0, int grid_Y0, int grid_cw)
 {
     const int cy0 = std::max(Y0, sub_y0_), cy1 = std::min(Y0 + H, sub_y0_ + sub_h_);
     if (cy1 <= cy0 || W <= 0) return -1;
@@ -148,6 +149,10 @@ int PyramidEngine::add_rect(int img_index, int X0, int Y0, int W, int H, int tlx
     t.roi_w = roi_w;
     t.roi_h = roi_h;
     t.packed = packed_ ? 1 : 0;
+    if (need_grid && g_.nb >= 2) {  // cell (0, 0) of this tile inside the image's occupancy grid
+        t.need = need_grid + (size_t)((cy0 - grid_Y0) >> g_.nb) * grid_cw + ((X0 - grid_X0) >> g_.nb);
+        t.need_cw = grid_cw;
+    }
     tiles_.push_back(t);
     return (int)tiles_.size() - 1;
 }
@@ -796,12 +801,16 @@ void Composer::plan(const isb_camera* cams, const int* sizes_wh, int n, int* cor
         }
         std::vector<uint8_t> occ(occ_bytes, 0);
         {
-            DevBuf occ_dev, occ_tiles_dev;
             ImageDev* idp = static_cast<ImageDev*>(imgs_dev_.ensure(n * sizeof(ImageDev)));
             ISB_CUDA(cudaMemcpyAsync(idp, idev.data(), n * sizeof(ImageDev), cudaMemcpyHostToDevice, st));
-            OccTile* otp = static_cast<OccTile*>(occ_tiles_dev.ensure(n * sizeof(OccTile)));
+            OccTile* otp = static_cast<OccTile*>(occ_tiles_dev_.ensure(n * sizeof(OccTile)));
             ISB_CUDA(cudaMemcpyAsync(otp, occ_tiles.data(), n * sizeof(OccTile), cudaMemcpyHostToDevice, st));
-            uint8_t* od = static_cast<uint8_t*>(occ_dev.ensure(std::max<size_t>(occ_bytes, 1)));
+            // the valid occupancy stays on the device: every run ANDs it with the seam masks' support (launch_seam_need)
+            uint8_t* od = static_cast<uint8_t*>(occ_valid_dev_.ensure(std::max<size_t>(occ_bytes, 1)));
+            occ_w_dev_.ensure(std::max<size_t>(occ_bytes, 1));
+            ISB_CUDA(cudaMemsetAsync(need_dev_.ensure(std::max<size_t>(occ_bytes, 1)), 1, std::max<size_t>(occ_bytes, 1), st));
+            occ_max_cw_ = max_w >> g.nb;
+            occ_max_ch_ = max_h >> g.nb;
             ISB_CUDA(cudaMemsetAsync(od, 0, std::max<size_t>(occ_bytes, 1), st));
             for (int z0 = 0; z0 < n; z0 += 32768)
                 launch_occupancy(otp + z0, std::min(32768, n - z0), max_w, max_h, idp, g.nb, od, st);
@@ -831,7 +840,8 @@ void Composer::plan(const isb_camera* cams, const int* sizes_wh, int n, int* cor
                     hi = std::max(hi, col_hi[x1]);
                 }
                 const int t = eng_.add_rect(i, full[i].X0 + (cx << g.nb), full[i].Y0 + (lo << g.nb), (x1 - cx + 1) << g.nb,
-                                            (hi - lo + 1) << g.nb, img_[i].roi.x, img_[i].roi.y, img_[i].roi.w, img_[i].roi.h);
+                                            (hi - lo + 1) << g.nb, img_[i].roi.x, img_[i].roi.y, img_[i].roi.w, img_[i].roi.h,
+                                            need_dev_.as<uint8_t>() + occ_tiles[i].occ_off, full[i].X0, full[i].Y0, cw);
                 if (t >= 0) tiles_of_image_[i].push_back(t);
                 cx = x1 + 1;
             }
@@ -979,7 +989,10 @@ void Composer::run(const isb_image* imgs, const isb_gainmap* gains, const isb_ma
     // ---- stage 1: seam dilate + fused warp (kernel 1) ---------------------------------------
     ISB_CUDA(cudaEventRecord(ev_[1], st));
     launch_dilate_seams(idp, n, max_mw, max_mh, st);
-    launch_warp_tiles_packed(eng_.warp_work_dev(), (int)eng_.warp_work().size(), eng_.tiles_dev(), idp, st);
+    if (seams && eng_.geom().nb >= 2)
+        launch_seam_need(occ_tiles_dev_.as<OccTile>(), n, occ_max_cw_, occ_max_ch_, idp, eng_.geom().nb, occ_valid_dev_.as<uint8_t>(),
+                         occ_w_dev_.as<uint8_t>(), need_dev_.as<uint8_t>(), st);
+    launch_warp_tiles_packed(eng_.warp_work_dev(), (int)eng_.warp_work().size(), eng_.tiles_dev(), idp, eng_.geom().nb, st);
     // ---- stage 2: pyramids (kernel 2) ---------------------------------------------------------
     ISB_CUDA(cudaEventRecord(ev_[2], st));
     eng_.build_pyramids(0, (int)eng_.tiles().size(), st);
