@@ -78,12 +78,14 @@ struct DstDev {
     const int* cell_tiles;
     int row0, row1;            // level-0 rows [row0,row1) this process owns (strip)
     int packed0;               // all tiles carry the byte-packed level 0 (fused composer)
+    int max_cell_tiles;        // longest tile list of any macro cell
 };
 
 struct OutDev {
     uint8_t* out8; long long pitch8;     // 8UC3 interleaved, may be null
     uint8_t* mask; long long mpitch;     // 8UC1, may be null
     int16_t* out16; long long pitch16;   // 16SC3 interleaved (bytes pitch), may be null
+    int fast8;                           // set by the launcher: the packed 8-bit store path applies
 };
 
 }  // namespace isb

@@ -306,6 +306,8 @@ void PyramidEngine::blend(const OutDev& out, cudaStream_t st)
         for (const TileDev& T : tiles_)
             for (int cy = T.y0 >> nb; cy < (T.y0 + T.h) >> nb; ++cy)
                 for (int cx = T.x0 >> nb; cx < (T.x0 + T.w) >> nb; ++cx) ++start[cy * dst_.cells_x + cx + 1];
+        dst_.max_cell_tiles = 0;
+        for (int i = 0; i < ncell; ++i) dst_.max_cell_tiles = std::max(dst_.max_cell_tiles, start[i + 1]);
         for (int i = 0; i < ncell; ++i) start[i + 1] += start[i];
         std::vector<int> fill(start.begin(), start.end() - 1), list(std::max(start[ncell], 1));
         for (int t = 0; t < (int)tiles_.size(); ++t) {  // ascending t == feed order
