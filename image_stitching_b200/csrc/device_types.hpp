@@ -43,10 +43,10 @@ struct TileDev {
     int img;                 // index into ImageDev[] (fused path) or -1 (classic feed)
     int left, top;           // ROI top-left relative to the tile origin (copyMakeBorder's left/top)
     int roi_w, roi_h;        // warped image size (tile px outside are REFLECT padding, weight 0)
-    // fused path with seam masks: need[cy * need_cw + cx] != 0 iff macro cell (cx, cy) of this tile lies within 4 cells
-    // of a cell in which the blend weight (valid & seam) can be non-zero; other cells never reach the output and the
-    // warp kernel zero-fills them instead of computing them.  Refreshed on the device every run.  nullptr: no map.
-    const uint8_t* need;
+    // fused path with seam masks: need[cy * need_cw + cx] == generation of the current run iff macro cell (cx, cy) of this
+    // tile lies within 4 cells of a cell in which the blend weight (valid & seam) can be non-zero; other cells never reach
+    // the output and the warp kernel zero-fills them instead of computing them.  Stamped on the device every run.
+    const uint32_t* need;
     int need_cw;
     // Fused path (`packed` != 0): the warped image is 8-bit, so every Gaussian level stays in [0,255] and is stored
     // byte-packed, one uint32 per pixel = b | g<<8 | r<<16 (| m<<24 at level 0, m = the 8-bit blend mask, whose

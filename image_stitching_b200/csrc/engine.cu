@@ -134,7 +134,7 @@ int PyramidEngine::add_tile(int img_index, int w, int h, int tlx, int tly)
 }
 
 int PyramidEngine::add_rect(int img_index, int X0, int Y0, int W, int H, int tlx, int tly, int roi_w, int roi_h,
-                            const uint8_t* need_grid, int grid_X0, int grid_Y0, int grid_cw)
+                            const uint32_t* need_grid, int grid_X0, int grid_Y0, int grid_cw)
 {
     const int cy0 = std::max(Y0, sub_y0_), cy1 = std::min(Y0 + H, sub_y0_ + sub_h_);
     if (cy1 <= cy0 || W <= 0) return -1;
@@ -809,8 +809,9 @@ void Composer::plan(const isb_camera* cams, const int* sizes_wh, int n, int* cor
             ISB_CUDA(cudaMemcpyAsync(otp, occ_tiles.data(), n * sizeof(OccTile), cudaMemcpyHostToDevice, st));
             // the valid occupancy stays on the device: every run ANDs it with the seam masks' support (launch_seam_need)
             uint8_t* od = static_cast<uint8_t*>(occ_valid_dev_.ensure(std::max<size_t>(occ_bytes, 1)));
-            occ_w_dev_.ensure(std::max<size_t>(occ_bytes, 1));
-            ISB_CUDA(cudaMemsetAsync(need_dev_.ensure(std::max<size_t>(occ_bytes, 1)), 1, std::max<size_t>(occ_bytes, 1), st));
+            ISB_CUDA(cudaMemsetAsync(need_dev_.ensure(std::max<size_t>(occ_bytes, 1) * sizeof(uint32_t)), 0,
+                                     std::max<size_t>(occ_bytes, 1) * sizeof(uint32_t), st));
+            need_gen_ = 0;
             occ_max_cw_ = max_w >> g.nb;
             occ_max_ch_ = max_h >> g.nb;
             ISB_CUDA(cudaMemsetAsync(od, 0, std::max<size_t>(occ_bytes, 1), st));
@@ -843,7 +844,7 @@ void Composer::plan(const isb_camera* cams, const int* sizes_wh, int n, int* cor
                 }
                 const int t = eng_.add_rect(i, full[i].X0 + (cx << g.nb), full[i].Y0 + (lo << g.nb), (x1 - cx + 1) << g.nb,
                                             (hi - lo + 1) << g.nb, img_[i].roi.x, img_[i].roi.y, img_[i].roi.w, img_[i].roi.h,
-                                            need_dev_.as<uint8_t>() + occ_tiles[i].occ_off, full[i].X0, full[i].Y0, cw);
+                                            need_dev_.as<uint32_t>() + occ_tiles[i].occ_off, full[i].X0, full[i].Y0, cw);
                 if (t >= 0) tiles_of_image_[i].push_back(t);
                 cx = x1 + 1;
             }
@@ -993,8 +994,8 @@ void Composer::run(const isb_image* imgs, const isb_gainmap* gains, const isb_ma
     launch_dilate_seams(idp, n, max_mw, max_mh, st);
     if (seams && eng_.geom().nb >= 2)
         launch_seam_need(occ_tiles_dev_.as<OccTile>(), n, occ_max_cw_, occ_max_ch_, idp, eng_.geom().nb, occ_valid_dev_.as<uint8_t>(),
-                         occ_w_dev_.as<uint8_t>(), need_dev_.as<uint8_t>(), st);
-    launch_warp_tiles_packed(eng_.warp_work_dev(), (int)eng_.warp_work().size(), eng_.tiles_dev(), idp, eng_.geom().nb, st);
+                         need_dev_.as<uint32_t>(), ++need_gen_, st);
+    launch_warp_tiles_packed(eng_.warp_work_dev(), (int)eng_.warp_work().size(), eng_.tiles_dev(), idp, eng_.geom().nb, need_gen_, st);
     // ---- stage 2: pyramids (kernel 2) ---------------------------------------------------------
     ISB_CUDA(cudaEventRecord(ev_[2], st));
     eng_.build_pyramids(0, (int)eng_.tiles().size(), st);

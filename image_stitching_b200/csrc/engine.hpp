@@ -87,7 +87,7 @@ public:
     // Same for an explicit rectangle (padded-ROI coordinates, on the 2^nb grid) of the image whose warped ROI
     // has its top-left at (tlx, tly) in panorama coordinates.
     int add_rect(int img_index, int X0, int Y0, int W, int H, int tlx, int tly, int roi_w, int roi_h,
-                 const uint8_t* need_grid = nullptr, int grid_X0 = 0, int grid_Y0 = 0, int grid_cw = 0);
+                 const uint32_t* need_grid = nullptr, int grid_X0 = 0, int grid_Y0 = 0, int grid_cw = 0);
     // pyrDown l -> l+1 has an even output width, so the register-rolling kernel applies
     bool fast_down(int l) const { return l + 1 < g_.nb; }
     static int fast_rows(int l) { return l == 0 ? kFastDownRowsDefault : kFastDownRowsCoarse; }
@@ -229,9 +229,10 @@ private:
     Arena tables_;              // trig tables (static per plan)
     Arena dyn_;                 // per-run uploads: sources, gains, seam masks, their coefficient tables
     DevBuf imgs_dev_, counts_dev_, out8_, outm_, out16_;
-    // seam-aware culling: plan-time valid occupancy per macro cell (device), per-run weight occupancy and its dilation
-    DevBuf occ_valid_dev_, occ_w_dev_, need_dev_, occ_tiles_dev_;
+    // seam-aware culling: plan-time valid occupancy per macro cell (device), per-run map of needed cells
+    DevBuf occ_valid_dev_, need_dev_, occ_tiles_dev_;
     int occ_max_cw_ = 0, occ_max_ch_ = 0;
+    uint32_t need_gen_ = 0;  // run counter stamped into the need map
     std::vector<unsigned long long> valid_counts_;
     cudaEvent_t ev_[8] = {};
     bool ev_init_ = false;

@@ -51,11 +51,13 @@ void launch_occupancy(const OccTile* tiles_dev, int n_tiles, int max_w, int max_
 // cv::dilate(3x3) of every image's seam mask in one launch: imgs[i].seam_raw -> imgs[i].seam
 void launch_dilate_seams(const ImageDev* imgs_dev, int n_img, int max_w, int max_h, cudaStream_t st);
 // fused warp -> packed level 0
-void launch_warp_tiles_packed(const WorkItem* work, int n_work, const TileDev* tiles, const ImageDev* imgs, int nb, cudaStream_t st);
-// per-run seam-aware culling: occ_w = valid occupancy & "the upsampled dilated seam mask can be non-zero in the cell";
-// need = occ_w dilated by 4 cells.  One OccTile per image (its full feed() tile on the 2^nb grid).
+void launch_warp_tiles_packed(const WorkItem* work, int n_work, const TileDev* tiles, const ImageDev* imgs, int nb, uint32_t gen,
+                              cudaStream_t st);
+// per-run seam-aware culling: every macro cell that holds a valid pixel (plan-time occupancy) and in which the upsampled
+// dilated seam mask can be non-zero stamps `gen` into need[] for all cells within 4 cells of it.  One OccTile per image
+// (its full feed() tile on the 2^nb grid).
 void launch_seam_need(const OccTile* tiles_dev, int n_tiles, int max_cw, int max_ch, const ImageDev* imgs, int nb,
-                      const uint8_t* occ_valid, uint8_t* occ_w, uint8_t* need, cudaStream_t st);
+                      const uint8_t* occ_valid, uint32_t* need, uint32_t gen, cudaStream_t st);
 // register-rolling separable pyrDown, 2 outputs per thread (packed or planar storage)
 void launch_pyrdown_fast(const WorkItem* work, int n_work, const TileDev* tiles, int level, bool packed, int rows_per_warp,
                          cudaStream_t st);
