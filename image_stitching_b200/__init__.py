@@ -658,8 +658,10 @@ class Composer:
         self.dst_roi = tuple(roi)
         return self.corners, self.sizes, self.dst_roi
 
-    def run(self, images, gains=None, seam_masks=None, out=None, out_mask=None, out16=None, want16=False):
-        """images: list of HxWx3 uint8 (numpy or torch.cuda).  Outputs are allocated (numpy) unless given."""
+    def run(self, images, gains=None, seam_masks=None, out=None, out_mask=None, out16=None, want16=False, out_pitch=None,
+            mask_pitch=None):
+        """images: list of HxWx3 uint8 (numpy or torch.cuda).  Outputs are allocated (numpy) unless given; out_pitch /
+        mask_pitch (bytes) describe caller buffers whose rows are wider than the panorama."""
         n = self.n
         keep = []
         ia = (_Image * n)()
@@ -699,9 +701,9 @@ class Composer:
             out16 = np.zeros((h, w, 3), np.int16)
         pano = _Pano()
         pano.data, k1 = _ptr(out)
-        pano.pitch = w * 3
+        pano.pitch = w * 3 if out_pitch is None else int(out_pitch)
         pano.mask, k2 = _ptr(out_mask)
-        pano.mask_pitch = w
+        pano.mask_pitch = w if mask_pitch is None else int(mask_pitch)
         if out16 is not None:
             pano.data16, k3 = _ptr(out16)
             pano.pitch16 = w * 6

@@ -1031,6 +1031,9 @@ void Composer::run(const isb_image* imgs, const isb_gainmap* gains, const isb_ma
             o.out16 = reinterpret_cast<int16_t*>(static_cast<char*>(out16_.ensure((size_t)o.pitch16 * std::max(oy1 - oy0, 1))) - (long long)(oy0 - sub0) * o.pitch16);
         }
     }
+    // strip-sharded runs usually write into rank 0's panorama over NVLink (peer-mapped pointers cannot be told apart from
+    // local ones reliably): their stores go out as staged 16-byte vectors; a single GPU is served better by direct stores
+    o.peer = d8 && cfg_.strip_count > 1;
     eng_.blend(o, st);
     // ---- stage 4: results to the host ---------------------------------------------------------
     ISB_CUDA(cudaEventRecord(ev_[4], st));

@@ -418,3 +418,27 @@ def test_simple_blenders_vs_oracle_wraparound_and_contract():
     r1, m1 = b.blend()
     r2, m2 = o.blend()
     assert np.array_equal(m1, m2) and np.array_equal(r1, r2)
+
+
+@pytest.mark.parametrize("aligned", [True, False])
+def test_compose_8bit_device_output_paths(aligned, monkeypatch):
+    """8UC3 + mask only, device-resident: the packed 16-bit stores and (16-byte aligned pitches) the shared-memory staged
+    vector stores of the level-0 blend kernel, against the generic path that the 16SC3 request of the other tests takes."""
+    torch = pytest.importorskip("torch")
+    if aligned:  # the staged path is reserved for peer-memory outputs (test_gpu_multi.py); force it on local memory here
+        monkeypatch.setenv("ISB_STAGED_STORES", "1")
+    rig, imgs, gains, nb = make_case("cfg2", 8, 5)
+    seams = seam_masks_oracle(rig)
+    ref = isb.compose(imgs, rig.Ks, rig.Rs, rig.scale, rig.warp, nb, gains, seams)  # generic stores (16SC3 requested)
+    c = isb.Composer(rig.warp, rig.scale, nb)
+    c.plan(isb.cameras_from_KR(rig.Ks, rig.Rs), [(rig.W, rig.H)] * rig.n)
+    x, y, w, h = c.dst_roi
+    p8 = (w * 3 + 15) // 16 * 16 + (0 if aligned else 2)
+    pm = (w + 15) // 16 * 16 + (0 if aligned else 2)
+    o8 = torch.full((h, p8), 7, dtype=torch.uint8, device="cuda")
+    om = torch.full((h, pm), 7, dtype=torch.uint8, device="cuda")
+    c.run([torch.from_numpy(im).cuda() for im in imgs], gains, seams, out=o8, out_mask=om, out_pitch=p8, mask_pitch=pm)
+    torch.cuda.synchronize()
+    o8, om = o8.cpu().numpy(), om.cpu().numpy()
+    assert np.array_equal(o8[:, :w * 3].reshape(h, w, 3), ref["result8"]) and np.array_equal(om[:, :w], ref["mask"])
+    assert (o8[:, w * 3:] == 7).all() and (om[:, w:] == 7).all()  # nothing written beyond the panorama's columns
