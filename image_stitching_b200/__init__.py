@@ -735,6 +735,35 @@ def compose(images, Ks, Rs, scale, warp, num_bands, gains=None, seam_masks=None,
     return c.run(images, gains, seam_masks, want16=want16)
 
 
+def compose_with_blender(images, Ks, Rs, scale, warp, blender, gains=None, seam_masks=None):
+    """The compositing loop (image_stitching.cpp:1086-1229) call by call through the C ABI mirrors, for any blender with the
+    prepare / feed / blend contract (MultiBandBlender, FeatherBlender, Blender_createDefault(BLENDER_NO)): warper.warp of the
+    image and of the all-255 mask, compensator.apply, convertTo(16S), dilate + INTER_LINEAR_EXACT resize + AND, feed, blend."""
+    warper = RotationWarper(warp, scale)
+    corners, sizes = [], []
+    for im, K, R in zip(images, Ks, Rs):
+        h, w = _shape(im)[:2]
+        x, y, rw, rh = warper.warpRoi((w, h), K, R)
+        corners.append((x, y))
+        sizes.append((rw, rh))
+    comp = None
+    if gains is not None:
+        comp = BlocksGainCompensator(64, 64, 1)
+        comp.setMatGains(gains)
+    blender.prepare(corners, sizes)
+    for i, (im, K, R) in enumerate(zip(images, Ks, Rs)):
+        _, img_warped = warper.warp(im, K, R, INTER_LINEAR, BORDER_REFLECT)
+        _, mask_warped = warper.warp(np.full(_shape(im)[:2], 255, np.uint8), K, R, INTER_NEAREST, BORDER_CONSTANT)
+        if comp is not None:
+            img_warped = comp.apply(i, corners[i], img_warped, mask_warped)
+        if seam_masks is not None:
+            mask_warped = seam_mask_apply(seam_masks[i], mask_warped)
+        blender.feed(img_warped.astype(np.int16), mask_warped, corners[i])
+    result, result_mask = blender.blend()
+    return dict(corners=corners, sizes=sizes, dst_roi=tuple(resultRoi(corners, sizes)), result16=result,
+                result8=np.clip(result, 0, 255).astype(np.uint8), mask=result_mask)
+
+
 def strip_rows(padded_h, final_h, num_bands, index, count):
     a, b = C.c_int(0), C.c_int(0)
     _chk(lib().isb_strip_rows(int(padded_h), int(final_h), int(num_bands), int(index), int(count), C.byref(a), C.byref(b)))

@@ -66,9 +66,15 @@ def seam_masks_cv(kind, scale, Ks, Rs, W, H, seam_div=8):
     return out
 
 
+def feather_sharpness(dst_w, dst_h, blend_strength=5.0):
+    """fb->setSharpness(1.f / blend_width), blend_width = sqrt(dst_area) * blend_strength / 100 (image_stitching.cpp:1177-1190)."""
+    return float(np.float32(1.0) / (np.sqrt(np.float32(dst_w * dst_h)) * np.float32(blend_strength) / np.float32(100.0)))
+
+
 def compose_cv(images, Ks, Rs, scale, kind, nb, gains=None, seam_masks=None, keep_stages=False,
-               timings=None):
-    """Mirror of the compositing loop.  Returns dict(corners, sizes, dst_roi, result16, result8, mask)."""
+               timings=None, blend_type="multiband", sharpness=None):
+    """Mirror of the compositing loop.  Returns dict(corners, sizes, dst_roi, result16, result8, mask).
+    blend_type: "multiband" (nb bands), "feather" (sharpness, default by the reference's rule) or "no"."""
     n = len(images)
     warper = make_warper(kind, scale)
     corners, sizes = [], []
@@ -81,8 +87,13 @@ def compose_cv(images, Ks, Rs, scale, kind, nb, gains=None, seam_masks=None, kee
     if gains is not None:
         comp = cv2.detail_BlocksGainCompensator(64, 64, 1)
         comp.setMatGains([np.ascontiguousarray(g, dtype=np.float32) for g in gains])
-    blender = cv2.detail_MultiBandBlender(0, int(nb))
     dst_roi = cv2.detail.resultRoi(corners=corners, sizes=sizes)
+    if blend_type == "multiband":
+        blender = cv2.detail_MultiBandBlender(0, int(nb))
+    elif blend_type == "feather":
+        blender = cv2.detail_FeatherBlender(feather_sharpness(dst_roi[2], dst_roi[3]) if sharpness is None else float(sharpness))
+    else:
+        blender = cv2.detail.Blender_createDefault(cv2.detail.Blender_NO)
     blender.prepare(dst_roi)
     stages = []
     tm = dict(warp_img=0.0, warp_mask=0.0, gain=0.0, to16s=0.0, seam=0.0, feed=0.0, blend=0.0)

@@ -101,6 +101,14 @@ def simple_blenders():
         out[tag + "_result16"], out[tag + "_mask"] = r, rm
     out["wm0"] = cv2.detail.createWeightMap(masks[0], 0.02, None)
     out["wm_full"] = cv2.detail.createWeightMap(np.full((40, 50), 255, np.uint8), 0.02, None)
+    # the whole loop with blend_type feather / no on a small rig (sharpness by the reference's rule, blend_strength 5)
+    rig, imgs, gains, nb = make_case("cfg2", 16, 3)
+    seams = cvr.seam_masks_cv(rig.warp, rig.scale, rig.Ks, rig.Rs, rig.W, rig.H)
+    for tag in ("feather", "no"):
+        ref = cvr.compose_cv(imgs, rig.Ks, rig.Rs, rig.scale, rig.warp, nb, gains, seams, blend_type=tag)
+        out["loop_" + tag + "_result16"], out["loop_" + tag + "_mask"] = ref["result16"], ref["mask"]
+        out["loop_dst_roi"] = np.array(ref["dst_roi"], np.int32)
+    out["loop_sharpness"] = np.array(cvr.feather_sharpness(ref["dst_roi"][2], ref["dst_roi"][3]), np.float32)
     np.savez_compressed(os.path.join(OUT, "simple_blend.npz"), **out)
     print("simple blenders written")
 

@@ -442,3 +442,22 @@ def test_compose_8bit_device_output_paths(aligned, monkeypatch):
     o8, om = o8.cpu().numpy(), om.cpu().numpy()
     assert np.array_equal(o8[:, :w * 3].reshape(h, w, 3), ref["result8"]) and np.array_equal(om[:, :w], ref["mask"])
     assert (o8[:, w * 3:] == 7).all() and (om[:, w:] == 7).all()  # nothing written beyond the panorama's columns
+
+
+@pytest.mark.parametrize("tag", ["feather", "no"])
+def test_loop_with_simple_blenders(tag):
+    """The compositing loop call by call through the C ABI with blend_type feather / no (image_stitching.cpp:1175-1191):
+    bit-exact against the same loop composed from the oracle, and within the north-star bar of the cv2 loop vectors."""
+    from test_oracle_golden import oracle_loop_with_blender
+    g = np.load(os.path.join(GOLD, "simple_blend.npz"))
+    rig, imgs, gains, nb = make_case("cfg2", 16, 3)
+    seams = seam_masks_oracle(rig)
+    sharp = float(g["loop_sharpness"])
+    gpu_b = isb.FeatherBlender(sharp) if tag == "feather" else isb.Blender_createDefault(isb.BLENDER_NO)
+    out = isb.compose_with_blender(imgs, rig.Ks, rig.Rs, rig.scale, rig.warp, gpu_b, gains, seams)
+    ref = oracle_loop_with_blender(rig, imgs, gains, seams, orc.SimpleBlender(1 if tag == "feather" else 0, sharp))
+    assert tuple(out["dst_roi"]) == tuple(ref["dst_roi"]) == tuple(g["loop_dst_roi"])
+    assert np.array_equal(out["mask"], ref["mask"]) and np.array_equal(out["result16"], ref["result16"])
+    assert np.array_equal(out["mask"], g["loop_" + tag + "_mask"])
+    cv8 = np.clip(g["loop_" + tag + "_result16"], 0, 255).astype(np.uint8)
+    assert np.abs(out["result8"].astype(int) - cv8.astype(int)).max() <= MAX_ABS and psnr(out["result8"], cv8) >= MIN_PSNR

@@ -89,3 +89,37 @@ def test_simple_blenders_match_golden():
             b.feed(img, m, c)
         r, rm = b.blend()
         assert np.array_equal(r, g[tag + "_result16"]) and np.array_equal(rm, g[tag + "_mask"]), tag
+
+
+def oracle_loop_with_blender(rig, imgs, gains, seams, blender):
+    """The compositing loop composed from the oracle's own functions for a prepare / feed / blend blender."""
+    corners, sizes = [], []
+    for K, R in zip(rig.Ks, rig.Rs):
+        x, y, w, h = orc.warp_roi(rig.warp, rig.scale, rig.W, rig.H, K, R)
+        corners.append((x, y))
+        sizes.append((w, h))
+    roi = orc.result_roi(corners, sizes)
+    blender.prepare(roi)
+    for i, (im, K, R) in enumerate(zip(imgs, rig.Ks, rig.Rs)):
+        _, iw = orc.warp(rig.warp, rig.scale, im, K, R, orc.LINEAR, 1)
+        _, mw = orc.warp(rig.warp, rig.scale, np.full(im.shape[:2], 255, np.uint8), K, R, orc.NEAREST, 0)
+        iw = orc.gain_apply(iw, gains[i])
+        up = orc.resize_linear_exact(orc.dilate3x3(seams[i]), mw.shape[1], mw.shape[0])
+        blender.feed(iw.astype(np.int16), up & mw, corners[i])
+    r, m = blender.blend()
+    return dict(dst_roi=roi, result16=r, mask=m, result8=np.clip(r, 0, 255).astype(np.uint8))
+
+
+@pytest.mark.parametrize("tag", ["feather", "no"])
+def test_loop_with_simple_blenders_matches_golden(tag):
+    """image_stitching.cpp:1086-1229 with blend_type feather / no, against the cv2-generated loop vectors.  The float
+    gain-map upsample is pinned to <= 1 ulp only, hence the <= 1 grey-level bar instead of equality."""
+    g = np.load(os.path.join(GOLD, "simple_blend.npz"))
+    rig, imgs, gains, nb = make_case("cfg2", 16, 3)
+    seams = seam_masks_oracle(rig)
+    b = orc.SimpleBlender(1 if tag == "feather" else 0, float(g["loop_sharpness"]))
+    out = oracle_loop_with_blender(rig, imgs, gains, seams, b)
+    assert out["dst_roi"] == tuple(g["loop_dst_roi"])
+    assert np.array_equal(out["mask"], g["loop_" + tag + "_mask"])
+    d = np.abs(out["result16"].astype(int) - g["loop_" + tag + "_result16"].astype(int))
+    assert d.max() <= 1 and (d > 0).mean() < 1e-3
