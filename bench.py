@@ -202,13 +202,15 @@ def run_ours(args, rank, world):
     padded_h = (ph + m_ - 1) // m_ * m_
     all_rows = strips.all_strip_rows(padded_h, ph, rig.nb, world)
     use_p2p = world > 1 and args.gather == "p2p"
+    # peer-memory gather: rows padded to 128 B so that the level-0 blend kernel's staged 16-byte stores apply over NVLink
+    p8, pm = (pw * 3, pw) if not use_p2p else ((pw * 3 + 127) // 128 * 128, (pw + 127) // 128 * 128)
     if use_p2p:
         # fused collapse + gather: rank 0 owns the panorama, the other ranks map it through CUDA IPC and their final
         # blend kernel stores its rows straight into rank 0's HBM over NVLink (no separate collective, no staging)
         ok = 1
         try:
             if rank == 0:
-                d_out, d_mask = isb.DevPtr.alloc((ph, pw, 3)), isb.DevPtr.alloc((ph, pw))
+                d_out, d_mask = isb.DevPtr.alloc((ph, p8)), isb.DevPtr.alloc((ph, pm))
                 handles = [d_out.ipc_handle(), d_mask.ipc_handle()]
             else:
                 handles = [None, None]
@@ -218,7 +220,7 @@ def run_ours(args, rank, world):
         dist.broadcast_object_list(handles, src=0)
         if rank != 0:
             try:
-                d_out, d_mask = isb.DevPtr.open_ipc(handles[0], (ph, pw, 3)), isb.DevPtr.open_ipc(handles[1], (ph, pw))
+                d_out, d_mask = isb.DevPtr.open_ipc(handles[0], (ph, p8)), isb.DevPtr.open_ipc(handles[1], (ph, pm))
             except Exception as e:  # noqa: BLE001
                 ok = 0
                 sys.stderr.write(f"rank {rank}: peer-memory import failed ({e}); falling back to NCCL gather\n")
@@ -226,6 +228,7 @@ def run_ours(args, rank, world):
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         use_p2p = bool(flag.item())  # every rank takes the same path
     if not use_p2p:
+        p8, pm = pw * 3, pw
         d_out = torch.zeros((ph, pw, 3), dtype=torch.uint8, device=dev)
         d_mask = torch.zeros((ph, pw), dtype=torch.uint8, device=dev)
 
@@ -236,7 +239,7 @@ def run_ours(args, rank, world):
             strips.gather_strips([d_out, d_mask], all_rows, rank, world)
 
     def step_device():
-        r = comp.run(d_imgs, d_gains, d_seams, out=d_out, out_mask=d_mask)
+        r = comp.run(d_imgs, d_gains, d_seams, out=d_out, out_mask=d_mask, out_pitch=p8, mask_pitch=pm)
         if world > 1:
             gather_strips(r["strip_rows"])
 
@@ -277,7 +280,7 @@ def run_ours(args, rank, world):
         for f in range(args.video + 5):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            comp.run(sets[f % 3], d_gains, d_seams, out=d_out, out_mask=d_mask)
+            comp.run(sets[f % 3], d_gains, d_seams, out=d_out, out_mask=d_mask, out_pitch=p8, mask_pitch=pm)
             e1.record(stream)
             e1.synchronize()
             if f >= 5:
@@ -290,14 +293,15 @@ def run_ours(args, rank, world):
     # per-stage device time (separate short loop so the event syncs do not perturb the timed region)
     stage = {}
     for _ in range(3):
-        comp.run(d_imgs, d_gains, d_seams, out=d_out, out_mask=d_mask)
+        comp.run(d_imgs, d_gains, d_seams, out=d_out, out_mask=d_mask, out_pitch=p8, mask_pitch=pm)
         for k, v in comp.timings().items():
             stage[k] = stage.get(k, 0.0) + v / 3
 
     # ---- e2e: pinned host buffers through the C ABI ---------------------------------------------------
     h_imgs = [torch.from_numpy(im).pin_memory() for im in imgs]
-    h_out = torch.zeros((ph, pw, 3), dtype=torch.uint8).pin_memory()
-    h_mask = torch.zeros((ph, pw), dtype=torch.uint8).pin_memory()
+    # (peer-memory gather: the host copies keep the padded row pitch of rank 0's panorama)
+    h_out = torch.zeros((ph, pw, 3) if p8 == pw * 3 else (ph, p8), dtype=torch.uint8).pin_memory()
+    h_mask = torch.zeros((ph, pm), dtype=torch.uint8).pin_memory()
     h2d = sum(int(t.numel()) for t in h_imgs) + sum(g.nbytes for g in gains) + sum(s.nbytes for s in seams)
     d2h = int(h_out.numel() + h_mask.numel()) if rank == 0 else 0
 
@@ -305,7 +309,7 @@ def run_ours(args, rank, world):
         if world == 1:
             comp.run([t.numpy() for t in h_imgs], gains, seams, out=h_out.numpy(), out_mask=h_mask.numpy())
         else:
-            r = comp.run([t.numpy() for t in h_imgs], gains, seams, out=d_out, out_mask=d_mask)
+            r = comp.run([t.numpy() for t in h_imgs], gains, seams, out=d_out, out_mask=d_mask, out_pitch=p8, mask_pitch=pm)
             gather_strips(r["strip_rows"])
             if use_p2p:
                 torch.cuda.synchronize()
@@ -360,7 +364,7 @@ def run_ours(args, rank, world):
         pipelined(2 * depth)
         ms_e2e = pipelined(e2e_steps)
         # the async path must give the same panorama as the device-resident one
-        comp.run(d_imgs, d_gains, d_seams, out=d_out, out_mask=d_mask)
+        comp.run(d_imgs, d_gains, d_seams, out=d_out, out_mask=d_mask, out_pitch=p8, mask_pitch=pm)
         torch.cuda.synchronize()
         e2e_extra.update({"pipeline_depth": depth,
                           "pipelined_equals_device_result": bool(torch.equal(slots[0][1], d_out.cpu()) and
@@ -409,7 +413,7 @@ def run_ours(args, rank, world):
         cv2.ocl.setUseOpenCL(False)
         tm = {}
         dt, mp, ref = cpu_reference_step(rig, imgs, gains, seams, timings=tm)
-        ours = comp.run(d_imgs, d_gains, d_seams, out=d_out, out_mask=d_mask)
+        ours = comp.run(d_imgs, d_gains, d_seams, out=d_out, out_mask=d_mask, out_pitch=p8, mask_pitch=pm)
         torch.cuda.synchronize()
         o8, om = d_out.cpu().numpy(), d_mask.cpu().numpy()
         d = np.abs(o8.astype(np.int16) - ref["result8"].astype(np.int16))
