@@ -11,6 +11,7 @@
 #include "../../include/image_stitching.h"
 #include "device_types.hpp"
 #include "geometry.hpp"
+#include "kernels.cuh"
 
 namespace isb {
 
@@ -90,8 +91,9 @@ public:
                  const uint32_t* need_grid = nullptr, int grid_X0 = 0, int grid_Y0 = 0, int grid_cw = 0);
     // pyrDown l -> l+1 has an even output width, so the register-rolling kernel applies
     bool fast_down(int l) const { return l + 1 < g_.nb; }
-    static int fast_rows(int l) { return l == 0 ? kFastDownRowsDefault : kFastDownRowsCoarse; }
-    static constexpr int kFastDownRowsDefault = 16, kFastDownRowsCoarse = 4;  // == kernels.cuh kFastDownRows / ...Small
+    // output rows per warp of the register-rolling pyrDown: long runs amortise the 3-row halo, short runs give the small
+    // levels more CTAs (they are latency-bound)
+    static int fast_rows(int l) { return l == 0 ? kFastDownRows : l == 1 ? kFastDownRowsLevel1 : kFastDownRowsSmall; }
     // Allocate pyramid storage for tiles [first, end) (device pointers filled in), upload descriptors.
     void commit_tiles(cudaStream_t st);
     // kernel 2 for tiles [first, end): all levels

@@ -70,8 +70,15 @@ void launch_blend_quad(const DstDev& dst, const TileDev* tiles, int level, const
 void count_launch();
 
 constexpr int kFastDownCols = 64;   // output columns per warp (2 per lane)
+#ifndef ISB_DOWN_ROWS_L1
+#define ISB_DOWN_ROWS_L1 4
+#endif
+#ifndef ISB_DOWN_ROWS_SMALL
+#define ISB_DOWN_ROWS_SMALL 4
+#endif
 constexpr int kFastDownRows = 16;   // output rows per warp (level 0 -> 1)
-constexpr int kFastDownRowsSmall = 4;  // ... at the coarser levels, where parallelism matters more than halo reuse
+constexpr int kFastDownRowsLevel1 = ISB_DOWN_ROWS_L1;    // level 1 -> 2
+constexpr int kFastDownRowsSmall = ISB_DOWN_ROWS_SMALL;  // coarser levels, where parallelism matters more than halo reuse
 constexpr int kFastDownWarps = 8;   // warps per CTA, stacked in y  -> CTA block = 64 x 128 outputs
 
 // geometry of the CTA blocks the planner must use when it builds work lists
