@@ -461,3 +461,29 @@ def test_loop_with_simple_blenders(tag):
     assert np.array_equal(out["mask"], g["loop_" + tag + "_mask"])
     cv8 = np.clip(g["loop_" + tag + "_result16"], 0, 255).astype(np.uint8)
     assert np.abs(out["result8"].astype(int) - cv8.astype(int)).max() <= MAX_ABS and psnr(out["result8"], cv8) >= MIN_PSNR
+
+
+def test_seam_aware_culling_follows_the_masks_of_each_run():
+    """The per-run need map must track the seam masks actually passed: same cached plan, different masks (incl. all-zero for
+    one image, none at all, and masks that keep only a corner), every run bit-exact against the oracle."""
+    rig, imgs, gains, nb = make_case("cfg2", 8, 5)
+    base = seam_masks_oracle(rig)
+    c = isb.Composer(rig.warp, rig.scale, nb, cache_plan=True)
+    c.plan(isb.cameras_from_KR(rig.Ks, rig.Rs), [(rig.W, rig.H)] * rig.n)
+    variants = []
+    variants.append(base)
+    v = [m.copy() for m in base]          # image 0 contributes nothing, image 1 keeps only its top-left corner,
+    v[0][:] = 0                           # image 2 takes everything it can see
+    v[1][:] = 0
+    v[1][: v[1].shape[0] // 3, : v[1].shape[1] // 3] = 255
+    v[2][:] = 255
+    variants.append(v)
+    variants.append(None)                 # no seam masks at all after runs with masks
+    variants.append([np.roll(m, m.shape[1] // 3, axis=1) for m in base])  # shifted support
+    variants.append(base)
+    for k, seams in enumerate(variants):
+        out = c.run(imgs, gains, seams, want16=True)
+        ref = orc.compose(imgs, rig.Ks, rig.Rs, rig.scale, rig.warp, nb, gains, seams)
+        assert np.array_equal(out["mask"], ref["mask"]), k
+        assert np.array_equal(out["result16"], ref["result16"]), k
+        assert np.array_equal(out["result8"], ref["result8"]), k
