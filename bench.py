@@ -323,7 +323,7 @@ def run_ours(args, rank, world):
                     h_mask.copy_(d_mask, non_blocking=True)
                     torch.cuda.synchronize()
 
-    e2e_steps = max(2, min(args.steps, 20))
+    e2e_steps = max(2, min(args.steps, 50))
     ms_e2e_sync = timed(step_e2e, e2e_steps, 2)  # one synchronous call per step: H2D -> kernels -> D2H back to back
     e2e_extra = {"sync_ms_per_step": ms_e2e_sync / e2e_steps, "pipeline_depth": 1}
     ms_e2e = ms_e2e_sync
