@@ -91,7 +91,7 @@ def lib():
     L.isb_composer_stage_name.restype = C.c_char_p
     L.isb_warper_get_scale.restype = C.c_float
     for f in ("isb_warper_create", "isb_compensator_create", "isb_blender_create", "isb_composer_create",
-              "isb_simple_blender_create"):
+              "isb_simple_blender_create", "isb_timelapser_create"):
         getattr(L, f).restype = C.c_void_p
     L.isb_simple_blender_create.argtypes = [C.c_int, C.c_float]
     L.isb_simple_blender_set_sharpness.argtypes = [C.c_void_p, C.c_float]
@@ -106,7 +106,7 @@ def lib():
     L.isb_quat_slerp.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
     L.isb_quat_from_axis_angle.argtypes = [C.c_void_p, C.c_double, C.c_void_p]
     for f in ("isb_warper_destroy", "isb_compensator_destroy", "isb_blender_destroy", "isb_composer_destroy",
-              "isb_simple_blender_destroy"):
+              "isb_simple_blender_destroy", "isb_timelapser_destroy"):
         getattr(L, f).argtypes = [C.c_void_p]
         getattr(L, f).restype = None
     _lib = L
@@ -610,6 +610,50 @@ def Blender_createDefault(btype, try_gpu=False):
     if btype == BLENDER_MULTI_BAND:
         return MultiBandBlender()
     raise IsbError(-5, "unknown blender type")
+
+
+TIMELAPSER_AS_IS, TIMELAPSER_CROP = 0, 1  # cv::detail::Timelapser::{AS_IS, CROP}
+
+
+class Timelapser:
+    """cv2.detail.Timelapser_createDefault(type): initialize / process / getDst (image_stitching.cpp:1194-1215)."""
+
+    def __init__(self, ttype=TIMELAPSER_AS_IS):
+        h = lib().isb_timelapser_create(int(ttype))
+        if not h:
+            raise IsbError(-5, lib().isb_last_error().decode())
+        self._h = C.c_void_p(h)
+        self.dst_roi = None
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().isb_timelapser_destroy(self._h)
+            self._h = None
+
+    def initialize(self, corners, sizes):
+        c = np.ascontiguousarray(corners, np.int32).reshape(-1, 2)
+        s = np.ascontiguousarray(sizes, np.int32).reshape(-1, 2)
+        roi = (C.c_int * 4)()
+        _chk(lib().isb_timelapser_initialize(self._h, c.ctypes.data_as(C.c_void_p), s.ctypes.data_as(C.c_void_p), len(c), roi))
+        self.dst_roi = tuple(roi)
+
+    def process(self, img, mask, tl):
+        if not _is_torch(img) and np.asarray(img).dtype != np.int16:
+            raise IsbError(-215, "Assertion failed: img.type() == CV_16SC3")
+        ip, _i = _ptr(img)
+        h, w = _shape(img)[:2]
+        _chk(lib().isb_timelapser_process(self._h, C.c_void_p(ip), C.c_size_t(w * 6), w, h, int(tl[0]), int(tl[1])))
+
+    def getDst(self):
+        w, h = self.dst_roi[2], self.dst_roi[3]
+        out = np.zeros((h, w, 3), np.int16)
+        if w > 0 and h > 0:
+            _chk(lib().isb_timelapser_get_dst(self._h, out.ctypes.data_as(C.c_void_p), C.c_size_t(w * 6)))
+        return out
+
+
+def Timelapser_createDefault(ttype):
+    return Timelapser(ttype)
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -15,6 +15,7 @@ struct isb_warper { Warper impl; isb_warper(int k, float s) : impl(k, s) {} };
 struct isb_compensator { Compensator impl; isb_compensator(int w, int h) : impl(w, h) {} };
 struct isb_blender { Blender impl; explicit isb_blender(int nb) : impl(nb) {} };
 struct isb_simple_blender { SimpleBlender impl; isb_simple_blender(int t, float s) : impl(t, s) {} };
+struct isb_timelapser { Timelapser impl; explicit isb_timelapser(int t) : impl(t) {} };
 struct isb_composer { Composer impl; explicit isb_composer(const isb_config& c) : impl(c) {} };
 
 static thread_local std::string t_error;
@@ -392,6 +393,33 @@ int isb_simple_blender_blend(isb_simple_blender* b, int16_t* dst, size_t dpitch,
 int isb_create_weight_map(const uint8_t* mask, size_t mpitch, int w, int h, float sharpness, float* weight, size_t wpitch)
 {
     return guarded([&] { SimpleBlender::weight_map(mask, mpitch, w, h, sharpness, weight, wpitch); });
+}
+
+// ---- Timelapser -------------------------------------------------------------------------------------
+isb_timelapser* isb_timelapser_create(int type)
+{
+    if (type != ISB_TIMELAPSER_AS_IS && type != ISB_TIMELAPSER_CROP) {
+        t_error = "isb_timelapser_create: type must be ISB_TIMELAPSER_AS_IS or ISB_TIMELAPSER_CROP";
+        return nullptr;
+    }
+    return new (std::nothrow) isb_timelapser(type);
+}
+void isb_timelapser_destroy(isb_timelapser* t) { delete t; }
+int isb_timelapser_initialize(isb_timelapser* t, const int* corners, const int* sizes, int n, int roi[4])
+{
+    return guarded([&] {
+        NOT_NULL(t); NOT_NULL(corners); NOT_NULL(sizes);
+        t->impl.initialize(corners, sizes, n);
+        if (roi) { roi[0] = t->impl.roi().x; roi[1] = t->impl.roi().y; roi[2] = t->impl.roi().w; roi[3] = t->impl.roi().h; }
+    });
+}
+int isb_timelapser_process(isb_timelapser* t, const int16_t* img, size_t ipitch, int w, int h, int tlx, int tly)
+{
+    return guarded([&] { NOT_NULL(t); t->impl.process(img, ipitch, w, h, tlx, tly); });
+}
+int isb_timelapser_get_dst(isb_timelapser* t, int16_t* dst, size_t dpitch)
+{
+    return guarded([&] { NOT_NULL(t); t->impl.get_dst(dst, dpitch); });
 }
 
 // ---- composer ---------------------------------------------------------------------------------------

@@ -209,6 +209,22 @@ private:
     DevBuf dst_, dmask_, dweight_, img_, mask_, wmap_, dist_;
 };
 
+// cv::detail::Timelapser / TimelapserCrop (image_stitching.cpp:1194-1215): every process() call clears the canvas and copies
+// the part of one warped image that lies inside dst_roi_ (AS_IS: resultRoi of all images; CROP: cv's Rect(max tl, min br)).
+class Timelapser {
+public:
+    explicit Timelapser(int type) : type_(type) {}
+    void initialize(const int* corners_xy, const int* sizes_wh, int n);
+    const Rect& roi() const { return roi_; }
+    void process(const int16_t* img, size_t ipitch, int w, int h, int tlx, int tly);
+    void get_dst(int16_t* dst, size_t dpitch);
+private:
+    int type_;
+    bool ready_ = false;
+    Rect roi_{};
+    DevBuf dst_, img_;
+};
+
 class Composer {
 public:
     explicit Composer(const isb_config& cfg) : cfg_(cfg) {}

@@ -9,6 +9,7 @@
 //            = min( x + prefmin_x'<=x (dv - x'),  -x + sufmin_x'>=x (dv + x') )    (one warp per row, shuffle scans)
 // A mask without any zero pixel gives an "infinite" distance; OpenCV then yields 65534 (or FLT_MAX with IPP): both
 // clamp to weight 1 for any sharpness >= 1.6e-5, which is asserted.
+#include <algorithm>
 #include <climits>
 
 #include "device_math.cuh"
@@ -255,6 +256,72 @@ void SimpleBlender::blend(int16_t* dst, size_t dpitch, uint8_t* dmask, size_t mp
     if (dmask && !dmk) copy2d(dmask, mpitch, om, (size_t)omp, w, h, st);
     ISB_CUDA(cudaStreamSynchronize(st));
     prepared_ = false;  // single use per prepare(), like the reference blenders
+}
+
+// ---- Timelapser ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) timelapse_copy_kernel(const int16_t* __restrict__ img, long long ipitch, int w, int h,
+                                                             int16_t* __restrict__ dst, int dw, int dh, int dx, int dy)
+{
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= w || y >= h) return;
+    const int X = dx + x, Y = dy + y;  // test_point(): dst_roi_.contains(tl + (x, y))
+    if ((unsigned)X >= (unsigned)dw || (unsigned)Y >= (unsigned)dh) return;
+    const int16_t* s = reinterpret_cast<const int16_t*>(reinterpret_cast<const char*>(img) + y * ipitch) + 3 * x;
+    int16_t* d = dst + ((long long)Y * dw + X) * 3;
+    d[0] = s[0]; d[1] = s[1]; d[2] = s[2];
+}
+
+void Timelapser::initialize(const int* corners, const int* sizes, int n)
+{
+    ISB_ASSERT(n > 0);
+    ISB_ASSERT(type_ == ISB_TIMELAPSER_AS_IS || type_ == ISB_TIMELAPSER_CROP);
+    if (type_ == ISB_TIMELAPSER_AS_IS) roi_ = result_roi(corners, sizes, n);
+    else {  // TimelapserCrop::initialize: Rect(Point(max tl), Point(min br)) - cv::Rect_(pt1, pt2) orders the corners itself
+        int tlx = INT_MIN, tly = INT_MIN, brx = INT_MAX, bry = INT_MAX;
+        for (int i = 0; i < n; ++i) {
+            tlx = std::max(tlx, corners[2 * i]); tly = std::max(tly, corners[2 * i + 1]);
+            brx = std::min(brx, corners[2 * i] + sizes[2 * i]); bry = std::min(bry, corners[2 * i + 1] + sizes[2 * i + 1]);
+        }
+        roi_ = Rect{std::min(tlx, brx), std::min(tly, bry), std::max(tlx, brx) - std::min(tlx, brx), std::max(tly, bry) - std::min(tly, bry)};
+    }
+    ready_ = true;
+}
+
+void Timelapser::process(const int16_t* img, size_t ipitch, int w, int h, int tlx, int tly)
+{
+    require_device();
+    if (!ready_) throw Error(ISB_ERR_ASSERT, "Assertion failed: initialize() must be called before process()");
+    if (!img) throw Error(ISB_ERR_NULL_PTR, "img is null");
+    ISB_ASSERT(w > 0 && h > 0 && ipitch >= (size_t)w * 6);
+    cudaStream_t st = current_stream();
+    const size_t n = (size_t)roi_.w * roi_.h * 6;
+    ISB_CUDA(cudaMemsetAsync(dst_.ensure(std::max<size_t>(n, 1)), 0, std::max<size_t>(n, 1), st));  // dst_.setTo(0)
+    if (roi_.w > 0 && roi_.h > 0) {
+        const int16_t* di = img;
+        size_t dip = ipitch;
+        if (mem_kind(img) != MemKind::Device) {
+            dip = (size_t)w * 6;
+            copy2d(img_.ensure(dip * h), dip, img, ipitch, dip, h, st);
+            di = img_.as<int16_t>();
+        }
+        timelapse_copy_kernel<<<dim3((w + 31) / 32, (h + 7) / 8), 256, 0, st>>>(di, (long long)dip, w, h, dst_.as<int16_t>(), roi_.w,
+                                                                               roi_.h, tlx - roi_.x, tly - roi_.y);
+        count_launch();
+        ISB_CUDA(cudaGetLastError());
+    }
+    ISB_CUDA(cudaStreamSynchronize(st));
+}
+
+void Timelapser::get_dst(int16_t* dst, size_t dpitch)
+{
+    require_device();
+    if (!ready_) throw Error(ISB_ERR_ASSERT, "Assertion failed: initialize() must be called before getDst()");
+    if (!dst) throw Error(ISB_ERR_NULL_PTR, "dst is null");
+    if (roi_.w <= 0 || roi_.h <= 0) return;
+    ISB_ASSERT(dpitch >= (size_t)roi_.w * 6);
+    cudaStream_t st = current_stream();
+    copy2d(dst, dpitch, dst_.ensure((size_t)roi_.w * roi_.h * 6), (size_t)roi_.w * 6, (size_t)roi_.w * 6, roi_.h, st);
+    ISB_CUDA(cudaStreamSynchronize(st));
 }
 
 }  // namespace isb

@@ -224,6 +224,18 @@ ISB_API int isb_simple_blender_blend(isb_simple_blender* b, int16_t* dst, size_t
 ISB_API int isb_create_weight_map(const uint8_t* mask, size_t mask_pitch, int w, int h, float sharpness, float* weight,
                                   size_t weight_pitch);
 
+/* cv::detail::Timelapser (image_stitching.cpp:1194-1215: Timelapser::createDefault(timelapse_type), initialize(corners,
+ * sizes), process(img_warped_s, ones, corners[img_idx]), getDst()) */
+enum { ISB_TIMELAPSER_AS_IS = 0, ISB_TIMELAPSER_CROP = 1 }; /* == cv::detail::Timelapser::{AS_IS, CROP} */
+typedef struct isb_timelapser isb_timelapser;
+ISB_API isb_timelapser* isb_timelapser_create(int type);
+ISB_API void isb_timelapser_destroy(isb_timelapser* t);
+ISB_API int isb_timelapser_initialize(isb_timelapser* t, const int* corners_xy, const int* sizes_wh, int n, int dst_roi_xywh[4]);
+/* process(img CV_16SC3, mask (ignored by OpenCV), tl): clears the canvas, copies the pixels of img that fall inside dst_roi */
+ISB_API int isb_timelapser_process(isb_timelapser* t, const int16_t* img, size_t img_pitch, int w, int h, int tl_x, int tl_y);
+/* getDst(): CV_16SC3 of dst_roi size */
+ISB_API int isb_timelapser_get_dst(isb_timelapser* t, int16_t* dst, size_t dst_pitch);
+
 /* ============================================================================================
  * Fused path: the whole loop image_stitching.cpp:1086-1229 (warp, mask, gain, ->16S, seam mask,
  * prepare, feed x n, blend, saturate to 8U) without materialising xmap/ymap or the intermediates.

@@ -288,3 +288,32 @@ def compose(images, Ks, Rs, scale, kind, nb, gains=None, seam_masks=None):
                       _p(out16), _p(out8), _p(om))
     return dict(corners=[tuple(int(v) for v in c) for c in corners], sizes=[tuple(int(v) for v in s) for s in sizes],
                 dst_roi=tuple(int(v) for v in roi), result16=out16, result8=out8, mask=om)
+
+
+class Timelapser:
+    """cv::detail::Timelapser (type 0, AS_IS) / TimelapserCrop (type 1) restated in numpy (image_stitching.cpp:1194-1215):
+    process() clears the canvas and copies the pixels of one 16SC3 image that fall inside dst_roi."""
+
+    def __init__(self, ttype):
+        self.ttype = int(ttype)
+
+    def initialize(self, corners, sizes):
+        if self.ttype == 0:
+            self.roi = result_roi(corners, sizes)
+        else:  # Rect(Point(max tl), Point(min br)): cv::Rect_(pt1, pt2) orders the two corners itself
+            tlx = max(c[0] for c in corners); tly = max(c[1] for c in corners)
+            brx = min(c[0] + s[0] for c, s in zip(corners, sizes)); bry = min(c[1] + s[1] for c, s in zip(corners, sizes))
+            self.roi = (min(tlx, brx), min(tly, bry), abs(brx - tlx), abs(bry - tly))
+        self.dst = np.zeros((self.roi[3], self.roi[2], 3), np.int16)
+
+    def process(self, img, mask, tl):
+        self.dst[:] = 0
+        h, w = img.shape[:2]
+        x0, y0 = tl[0] - self.roi[0], tl[1] - self.roi[1]
+        xa, ya = max(x0, 0), max(y0, 0)
+        xb, yb = min(x0 + w, self.roi[2]), min(y0 + h, self.roi[3])
+        if xb > xa and yb > ya:
+            self.dst[ya:yb, xa:xb] = img[ya - y0:yb - y0, xa - x0:xb - x0]
+
+    def getDst(self):
+        return self.dst

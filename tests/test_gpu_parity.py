@@ -487,3 +487,22 @@ def test_seam_aware_culling_follows_the_masks_of_each_run():
         assert np.array_equal(out["mask"], ref["mask"]), k
         assert np.array_equal(out["result16"], ref["result16"]), k
         assert np.array_equal(out["result8"], ref["result8"]), k
+
+
+@pytest.mark.parametrize("ttype", [0, 1])
+def test_timelapser_bit_exact(ttype):
+    """cv::detail::Timelapser / TimelapserCrop through the C ABI against the (cv2-pinned) numpy restatement."""
+    rng = np.random.default_rng(12)
+    for corners, sizes in [([(0, 0), (150, -30), (-77, 41)], [(300, 200), (257, 213), (190, 260)]),
+                           ([(0, 0), (20, 10), (-15, 25)], [(300, 200), (257, 213), (290, 160)])]:
+        a, b = isb.Timelapser_createDefault(ttype), orc.Timelapser(ttype)
+        a.initialize(corners, sizes)
+        b.initialize(corners, sizes)
+        assert tuple(a.dst_roi) == tuple(b.roi)
+        for (c, (sw, sh)) in zip(corners, sizes):
+            img = rng.integers(-300, 600, (sh, sw, 3)).astype(np.int16)
+            a.process(img, None, c)
+            b.process(img, None, c)
+            assert np.array_equal(a.getDst(), b.getDst()), (ttype, c)
+    with pytest.raises(isb.IsbError):
+        isb.Timelapser(0).process(np.zeros((4, 4, 3), np.int16), None, (0, 0))  # initialize() first

@@ -176,3 +176,22 @@ def test_feather_and_no_blender(cv2_parity):
         r, rm = b.blend(None, None)
         r2, rm2 = b2.blend()
         assert np.array_equal(r, r2) and np.array_equal(rm, rm2), (btype, sharp)
+
+
+def test_timelapser(cv2_parity):
+    """Timelapser::createDefault(AS_IS / CROP), initialize, process, getDst (image_stitching.cpp:1194-1215)."""
+    cv2 = cv2_parity
+    rng = np.random.default_rng(2)
+    for corners, sizes in [([(0, 0), (150, -30), (-77, 41)], [(300, 200), (257, 213), (190, 260)]),
+                           ([(0, 0), (20, 10), (-15, 25)], [(300, 200), (257, 213), (290, 160)])]:
+        for ttype in (0, 1):
+            a = cv2.detail.Timelapser_createDefault(ttype)
+            b = orc.Timelapser(ttype)
+            a.initialize(corners, sizes)
+            b.initialize(corners, sizes)
+            for (c, (sw, sh)) in zip(corners, sizes):
+                img = rng.integers(-300, 600, (sh, sw, 3)).astype(np.int16)
+                a.process(img, np.ones((sh, sw), np.uint8), c)
+                b.process(img, None, c)
+                ref = a.getDst().get()
+                assert ref.shape == b.getDst().shape and np.array_equal(ref, b.getDst()), (ttype, c)
