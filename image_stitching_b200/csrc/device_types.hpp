@@ -86,7 +86,7 @@ struct OutDev {
     uint8_t* mask; long long mpitch;     // 8UC1, may be null
     int16_t* out16; long long pitch16;   // 16SC3 interleaved (bytes pitch), may be null
     int fast8;                           // set by the launcher: the packed 8-bit store path applies
-    int vec16;                           // ... the output is peer memory and 16-byte aligned (staged vector stores)
+    int staged;                          // set by the launcher: strip-sharded output, staged vector stores (any alignment)
     int peer;                            // set by the composer: strip-sharded run, the output may live on another GPU
 };
 

@@ -420,12 +420,14 @@ def test_simple_blenders_vs_oracle_wraparound_and_contract():
     assert np.array_equal(m1, m2) and np.array_equal(r1, r2)
 
 
-@pytest.mark.parametrize("aligned", [True, False])
-def test_compose_8bit_device_output_paths(aligned, monkeypatch):
-    """8UC3 + mask only, device-resident: the packed 16-bit stores and (16-byte aligned pitches) the shared-memory staged
-    vector stores of the level-0 blend kernel, against the generic path that the 16SC3 request of the other tests takes."""
+@pytest.mark.parametrize("pad,staged", [(0, True), (2, False), (1, True), (1, False), (6, True), (13, True)])
+def test_compose_8bit_device_output_paths(pad, staged, monkeypatch):
+    """8UC3 + mask only, device-resident, rows wider than the panorama by `pad` bytes beyond a multiple of 16: the packed
+    2-byte stores (even pitches), the byte stores (odd pitches) and - forced here on local memory, normally reserved for the
+    strip-sharded peer-memory output - the shared-memory staged 16-byte stores at every alignment, against the generic path
+    that the 16SC3 request of the other tests takes."""
     torch = pytest.importorskip("torch")
-    if aligned:  # the staged path is reserved for peer-memory outputs (test_gpu_multi.py); force it on local memory here
+    if staged:
         monkeypatch.setenv("ISB_STAGED_STORES", "1")
     rig, imgs, gains, nb = make_case("cfg2", 8, 5)
     seams = seam_masks_oracle(rig)
@@ -433,8 +435,8 @@ def test_compose_8bit_device_output_paths(aligned, monkeypatch):
     c = isb.Composer(rig.warp, rig.scale, nb)
     c.plan(isb.cameras_from_KR(rig.Ks, rig.Rs), [(rig.W, rig.H)] * rig.n)
     x, y, w, h = c.dst_roi
-    p8 = (w * 3 + 15) // 16 * 16 + (0 if aligned else 2)
-    pm = (w + 15) // 16 * 16 + (0 if aligned else 2)
+    p8 = (w * 3 + 15) // 16 * 16 + pad
+    pm = (w + 15) // 16 * 16 + pad
     o8 = torch.full((h, p8), 7, dtype=torch.uint8, device="cuda")
     om = torch.full((h, pm), 7, dtype=torch.uint8, device="cuda")
     c.run([torch.from_numpy(im).cuda() for im in imgs], gains, seams, out=o8, out_mask=om, out_pitch=p8, mask_pitch=pm)
