@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 
@@ -203,6 +204,8 @@ void PyramidEngine::commit_tiles(cudaStream_t st)
         }
     }
     // work lists for the new tiles
+    last_fast_ = packed_ && first == 0;
+    for (const TileDev& T : tiles_) last_fast_ = last_fast_ && (T.w >> nb) >= 2;
     warp_work_.clear();
     for (auto& v : down_work_) v.clear();
     for (int t = first; t < end; ++t) {
@@ -280,7 +283,7 @@ void PyramidEngine::build_pyramids(int first, int end, cudaStream_t st)
     for (int l = 0; l < g_.nb; ++l) {
         const int n = (int)(down_off_[l + 1] - down_off_[l]);
         if (l == 0 && use_tma_) launch_pyrdown_tma(base + down_off_[l], n, tiles_dev(), tmaps_dev_.as<void>(), st);
-        else if (fast_down(l)) launch_pyrdown_fast(base + down_off_[l], n, tiles_dev(), l, packed_, fast_rows(l), st);
+        else if (fast_down(l)) launch_pyrdown_fast(base + down_off_[l], n, tiles_dev(), l, packed_, fast_rows(l), l + 1 == g_.nb, st);
         else launch_pyrdown_tiles(base + down_off_[l], n, tiles_dev(), l, st);
     }
 }
@@ -805,9 +808,10 @@ void Composer::plan(const isb_camera* cams, const int* sizes_wh, int n, int* cor
         {
             ImageDev* idp = static_cast<ImageDev*>(imgs_dev_.ensure(n * sizeof(ImageDev)));
             ISB_CUDA(cudaMemcpyAsync(idp, idev.data(), n * sizeof(ImageDev), cudaMemcpyHostToDevice, st));
+            last_idev_.clear();  // imgs_dev_ now holds the plan-time subset of the descriptors
             OccTile* otp = static_cast<OccTile*>(occ_tiles_dev_.ensure(n * sizeof(OccTile)));
             ISB_CUDA(cudaMemcpyAsync(otp, occ_tiles.data(), n * sizeof(OccTile), cudaMemcpyHostToDevice, st));
-            // the valid occupancy stays on the device: every run ANDs it with the seam masks' support (launch_seam_need)
+            // the valid occupancy stays on the device: every run ANDs it with the seam masks' support (launch_seam_prep)
             uint8_t* od = static_cast<uint8_t*>(occ_valid_dev_.ensure(std::max<size_t>(occ_bytes, 1)));
             ISB_CUDA(cudaMemsetAsync(need_dev_.ensure(std::max<size_t>(occ_bytes, 1) * sizeof(uint32_t)), 0,
                                      std::max<size_t>(occ_bytes, 1) * sizeof(uint32_t), st));
@@ -987,14 +991,19 @@ void Composer::run(const isb_image* imgs, const isb_gainmap* gains, const isb_ma
         }
     }
     ImageDev* idp = static_cast<ImageDev*>(imgs_dev_.ensure(n * sizeof(ImageDev)));
-    ISB_CUDA(cudaMemcpyAsync(idp, idev.data(), n * sizeof(ImageDev), cudaMemcpyHostToDevice, st));
+    // the descriptors hold pointers and sizes only: device-resident callers repeat them run after run, and the copy that is
+    // already on the device (stream-ordered behind the previous run) is then the one to use
+    if (last_idev_.size() != idev.size() || std::memcmp(last_idev_.data(), idev.data(), n * sizeof(ImageDev)) != 0) {
+        ISB_CUDA(cudaMemcpyAsync(idp, idev.data(), n * sizeof(ImageDev), cudaMemcpyHostToDevice, st));
+        last_idev_ = idev;
+    }
 
     // ---- stage 1: seam dilate + fused warp (kernel 1) ---------------------------------------
     ISB_CUDA(cudaEventRecord(ev_[1], st));
-    launch_dilate_seams(idp, n, max_mw, max_mh, st);
-    if (seams && eng_.geom().nb >= 2)
-        launch_seam_need(occ_tiles_dev_.as<OccTile>(), n, occ_max_cw_, occ_max_ch_, idp, eng_.geom().nb, occ_valid_dev_.as<uint8_t>(),
-                         need_dev_.as<uint32_t>(), ++need_gen_, st);
+    const bool cull = seams && eng_.geom().nb >= 2;
+    if (cull) ++need_gen_;
+    launch_seam_prep(idp, n, max_mw, max_mh, occ_tiles_dev_.as<OccTile>(), occ_max_cw_, occ_max_ch_, eng_.geom().nb,
+                     occ_valid_dev_.as<uint8_t>(), cull ? need_dev_.as<uint32_t>() : nullptr, need_gen_, st);
     launch_warp_tiles_packed(eng_.warp_work_dev(), (int)eng_.warp_work().size(), eng_.tiles_dev(), idp, eng_.geom().nb, need_gen_, st);
     // ---- stage 2: pyramids (kernel 2) ---------------------------------------------------------
     ISB_CUDA(cudaEventRecord(ev_[2], st));

@@ -89,8 +89,9 @@ public:
     // has its top-left at (tlx, tly) in panorama coordinates.
     int add_rect(int img_index, int X0, int Y0, int W, int H, int tlx, int tly, int roi_w, int roi_h,
                  const uint32_t* need_grid = nullptr, int grid_X0 = 0, int grid_Y0 = 0, int grid_cw = 0);
-    // pyrDown l -> l+1 has an even output width, so the register-rolling kernel applies
-    bool fast_down(int l) const { return l + 1 < g_.nb; }
+    // pyrDown l -> l+1 runs the register-rolling kernel: always when the output width is even (l + 1 < nb); the last level
+    // of packed tiles (odd widths possible) when every tile is at least two macro cells wide (last_fast_, commit_tiles)
+    bool fast_down(int l) const { return l + 1 < g_.nb || (last_fast_ && l >= 1); }
     // output rows per warp of the register-rolling pyrDown: long runs amortise the 3-row halo, short runs give the small
     // levels more CTAs (they are latency-bound)
     static int fast_rows(int l) { return l == 0 ? kFastDownRows : l == 1 ? kFastDownRowsLevel1 : kFastDownRowsSmall; }
@@ -120,6 +121,7 @@ private:
     Arena arena_;                 // fused path: one block for all tiles
     std::vector<DevBuf*> extra_;  // classic path: one allocation per late-added tile
     DevBuf tiles_dev_, warp_work_dev_, down_work_dev_, cells_dev_, dst_buf_, tmaps_dev_;
+    bool last_fast_ = false;
     bool use_tma_ = false;  // level 0 -> 1 pyrDown staged by TMA (packed tiles large enough for a full box)
     std::vector<WorkItem> warp_work_;
     std::vector<std::vector<WorkItem>> down_work_;  // per level, for tiles of the last commit
@@ -254,6 +256,8 @@ private:
     std::vector<unsigned long long> valid_counts_;
     cudaEvent_t ev_[8] = {};
     bool ev_init_ = false;
+    // descriptors of the last run as uploaded to imgs_dev_ (a run with identical descriptors skips the upload)
+    std::vector<ImageDev> last_idev_;
     float last_ms_[8] = {};
 public:
     ~Composer();

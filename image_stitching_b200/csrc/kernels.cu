@@ -10,6 +10,7 @@
 // None of this is a dense contraction, so no tensor cores: the kernels are HBM/LSU bound.
 #include <climits>
 #include <cstdint>
+#include <cstdlib>
 
 #include "kernels.cuh"
 #include "device_math.cuh"
@@ -25,6 +26,12 @@ long long launch_count(bool reset)
 }
 #define ISB_COUNT_LAUNCH() (++g_launches)
 void count_launch() { ++g_launches; }
+
+bool pdl_enabled()
+{
+    const char* e = getenv("ISB_PDL");  // read on every launch: a tuning switch, a few ns next to a launch
+    return !(e && e[0] == '0');
+}
 
 // ------------------------------------------------------------------------------------------------
 // classic API kernels
@@ -278,6 +285,7 @@ void launch_count_valid(const ImageDev* imgs_dev, int n_img, const int* roi_w_ho
 __global__ void __launch_bounds__(256) pyrdown_tiles_kernel(const WorkItem* __restrict__ work,
                                                             const TileDev* __restrict__ tiles, int l)
 {
+    pdl_prologue();
     const WorkItem wi = work[blockIdx.x];
     const TileDev& T = tiles[wi.tile];
     const int wl = T.w >> l, hl = T.h >> l, ow = wl >> 1, oh = hl >> 1;
@@ -326,8 +334,7 @@ __global__ void __launch_bounds__(256) pyrdown_tiles_kernel(const WorkItem* __re
 void launch_pyrdown_tiles(const WorkItem* work, int n_work, const TileDev* tiles, int level, cudaStream_t st)
 {
     if (n_work <= 0) return;
-    pyrdown_tiles_kernel<<<n_work, 256, 0, st>>>(work, tiles, level);
-    ISB_COUNT_LAUNCH();
+    launch_chained(pyrdown_tiles_kernel, dim3(n_work), dim3(256), 0, st, work, tiles, level);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -339,6 +346,7 @@ void launch_pyrdown_tiles(const WorkItem* work, int n_work, const TileDev* tiles
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) blend_level_kernel(DstDev D, const TileDev* __restrict__ tiles, int l, OutDev O)
 {
+    pdl_prologue();
     const int pw = D.pw >> l, ph = D.ph >> l;
     const int x = blockIdx.x * 32 + (threadIdx.x & 31);
     // only level 0 is restricted to the rows this process owns; coarser levels cover the whole (sub-)panorama
@@ -401,8 +409,7 @@ void launch_blend_level(const DstDev& dst, const TileDev* tiles, int level, cons
     const int y0 = level == 0 ? dst.row0 : 0, y1 = level == 0 ? min(dst.ph, dst.row1) : (dst.ph >> level);
     if (y1 <= y0 || pw <= 0) return;
     dim3 grid((pw + 31) / 32, (y1 - y0 + 7) / 8);
-    blend_level_kernel<<<grid, 256, 0, st>>>(dst, tiles, level, out);
-    ISB_COUNT_LAUNCH();
+    launch_chained(blend_level_kernel, grid, dim3(256), 0, st, dst, tiles, level, out);
 }
 
 }  // namespace isb

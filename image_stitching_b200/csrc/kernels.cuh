@@ -7,6 +7,39 @@
 namespace isb {
 
 long long launch_count(bool reset);
+void count_launch();
+
+// ---- programmatic dependent launch (PDL) of the composer's kernel chain ------------------------------------------
+// The fused step is a chain of 14+ kernels of which nine are tiny (coarse pyramid levels, seam maps).  Every kernel of
+// the chain starts with pdl_prologue(): it first releases its own dependents (so the next kernel's CTAs may become
+// resident while this one drains its last wave - they hold no resources a CTA of this grid still waits for, because the
+// trigger only fires once ALL CTAs of this grid have executed it) and then waits until the grid it depends on has
+// completed and flushed its memory.  Launched without the attribute (classic per-call API) both instructions are no-ops.
+bool pdl_enabled();  // ISB_PDL=0 turns the launch attribute off (A/B measurements)
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_prologue()
+{
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+// kernel<<<grid, block, smem, st>>>(args...) with programmatic stream serialization allowed
+template <typename... KArgs, typename... Args>
+inline void launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+    count_launch();
+}
+#endif
 
 // ---- classic per-call API ---------------------------------------------------------------------
 // RotationWarper::warp: dst(rect_h x rect_w, `ch` channels) from src via the separable-table inverse map.
@@ -48,26 +81,25 @@ void launch_blend_level(const DstDev& dst, const TileDev* tiles, int level, cons
 struct OccTile { int img; int left, top; int w, h; long long occ_off; };
 void launch_occupancy(const OccTile* tiles_dev, int n_tiles, int max_w, int max_h, const ImageDev* imgs, int nb,
                       uint8_t* occ, cudaStream_t st);
-// cv::dilate(3x3) of every image's seam mask in one launch: imgs[i].seam_raw -> imgs[i].seam
-void launch_dilate_seams(const ImageDev* imgs_dev, int n_img, int max_w, int max_h, cudaStream_t st);
 // fused warp -> packed level 0
 void launch_warp_tiles_packed(const WorkItem* work, int n_work, const TileDev* tiles, const ImageDev* imgs, int nb, uint32_t gen,
                               cudaStream_t st);
-// per-run seam-aware culling: every macro cell that holds a valid pixel (plan-time occupancy) and in which the upsampled
-// dilated seam mask can be non-zero stamps `gen` into need[] for all cells within 4 cells of it.  One OccTile per image
-// (its full feed() tile on the 2^nb grid).
-void launch_seam_need(const OccTile* tiles_dev, int n_tiles, int max_cw, int max_ch, const ImageDev* imgs, int nb,
-                      const uint8_t* occ_valid, uint32_t* need, uint32_t gen, cudaStream_t st);
+// per-run seam preparation in one launch: (1) cv::dilate(3x3) of every image's seam mask, imgs[i].seam_raw -> imgs[i].seam;
+// (2) seam-aware culling (need != nullptr): every macro cell that holds a valid pixel (plan-time occupancy) and in which the
+// upsampled dilated seam mask can be non-zero stamps `gen` into need[] for all cells within 4 cells of it.  One OccTile per
+// image (its full feed() tile on the 2^nb grid).
+void launch_seam_prep(const ImageDev* imgs_dev, int n_img, int max_mw, int max_mh, const OccTile* tiles_dev, int max_cw, int max_ch,
+                      int nb, const uint8_t* occ_valid, uint32_t* need, uint32_t gen, cudaStream_t st);
 // register-rolling separable pyrDown, 2 outputs per thread (packed or planar storage)
+// odd_width: the level's output width may be odd (last level of packed tiles at least two macro cells wide)
 void launch_pyrdown_fast(const WorkItem* work, int n_work, const TileDev* tiles, int level, bool packed, int rows_per_warp,
-                         cudaStream_t st);
+                         bool odd_width, cudaStream_t st);
 // TMA-staged level 0 -> 1 pyrDown of packed tiles: `tmaps` = one CUtensorMap per tile (level-0 plane), device memory
 void launch_pyrdown_tma(const WorkItem* work, int n_work, const TileDev* tiles, const void* tmaps, cudaStream_t st);
 constexpr int kTmaOutW = 64, kTmaOutH = 32;                          // outputs per CTA
 constexpr int kTmaBoxW = 2 * kTmaOutW + 8, kTmaBoxH = 2 * kTmaOutH + 3;  // 136 x 67 input box (x origin 2*ox0 - 4)
 // 2x2-quad accumulate + normalise + collapse for level < nb
 void launch_blend_quad(const DstDev& dst, const TileDev* tiles, int level, const OutDev& out, cudaStream_t st);
-void count_launch();
 
 constexpr int kFastDownCols = 64;   // output columns per warp (2 per lane)
 #ifndef ISB_DOWN_ROWS_L1
