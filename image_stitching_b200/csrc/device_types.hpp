@@ -66,6 +66,19 @@ struct TileDev {
 // A CTA-sized piece of work: block (bx, by) of tile `tile` at the kernel's level.
 struct WorkItem { int tile, bx, by, pad; };
 
+// Compact per-(tile, level) view used by kernel 3 on packed tiles: what a quad of level l needs from one covering tile.
+// Built once per plan for every CSR entry and level (DstDev::cdesc), so that the kernel reads ONE 48-byte record after
+// the cell list instead of chasing cell_tiles -> TileDev -> its per-level arrays.
+struct alignas(16) CellTile {
+    const uint32_t* p0;   // packed level l
+    const uint32_t* p1;   // packed level l + 1
+    const float* w0;      // f32 weights of level l (levels >= 1; level 0 carries them in the mask byte), pitch0 as well
+    int pitch0, pitch1;   // elements (a packed tile's weight plane has the pitch of its pixel plane)
+    int ox, oy;           // tile origin at level l
+    int wc, hc;           // size of level l + 1
+};
+static_assert(sizeof(CellTile) == 48, "kernel 3 moves a record as three 16-byte words");
+
 // Destination state of one blend (MultiBandBlender::prepare)
 struct DstDev {
     int nb;
@@ -76,6 +89,8 @@ struct DstDev {
     int cells_x, cells_y;      // macro cells of 2^nb x 2^nb level-0 px
     const int* cell_start;     // CSR: tiles covering each macro cell, ascending feed order
     const int* cell_tiles;
+    const CellTile* cdesc;     // packed tiles: record of CSR entry e at level l (< nb) = cdesc[l * n_entries + e]; else nullptr
+    int n_entries;
     int row0, row1;            // level-0 rows [row0,row1) this process owns (strip)
     int packed0;               // all tiles carry the byte-packed level 0 (fused composer)
     int max_cell_tiles;        // longest tile list of any macro cell

@@ -332,6 +332,26 @@ void PyramidEngine::blend(const OutDev& out, cudaStream_t st)
         ISB_CUDA(cudaMemcpyAsync(cd + start.size(), list.data(), list.size() * sizeof(int), cudaMemcpyHostToDevice, st));
         dst_.cell_start = cd;
         dst_.cell_tiles = cd + start.size();
+        dst_.cdesc = nullptr;
+        dst_.n_entries = start[ncell];
+        if (packed_ && nb > 0 && dst_.n_entries > 0) {
+            // compact per-(entry, level) records for kernel 3 (see CellTile)
+            std::vector<CellTile> desc((size_t)nb * dst_.n_entries);
+            for (int l = 0; l < nb; ++l)
+                for (int e = 0; e < dst_.n_entries; ++e) {
+                    const TileDev& T = tiles_[list[e]];
+                    CellTile& c = desc[(size_t)l * dst_.n_entries + e];
+                    c.p0 = T.P[l]; c.p1 = T.P[l + 1]; c.w0 = T.W[l];
+                    c.pitch0 = T.ppitch[l]; c.pitch1 = T.ppitch[l + 1];
+                    ISB_ASSERT(T.wpitch[l] == T.ppitch[l]);
+                    c.ox = T.x0 >> l; c.oy = T.y0 >> l;
+                    c.wc = T.w >> (l + 1); c.hc = T.h >> (l + 1);
+                }
+            CellTile* dd = static_cast<CellTile*>(cdesc_dev_.ensure(desc.size() * sizeof(CellTile)));
+            ISB_CUDA(cudaMemcpyAsync(dd, desc.data(), desc.size() * sizeof(CellTile), cudaMemcpyHostToDevice, st));
+            ISB_CUDA(cudaStreamSynchronize(st));  // `desc` is a local
+            dst_.cdesc = dd;
+        }
     }
     for (int l = nb; l >= 0; --l) {
         if (l < nb) launch_blend_quad(dst_, tiles_dev(), l, out, st);
@@ -784,7 +804,9 @@ void Composer::plan(const isb_camera* cams, const int* sizes_wh, int n, int* cor
         // keep OpenCV's border rules; the other cuts are too far from any non-zero weight to matter.
         struct FullTile { int X0, Y0, W, H; };
         std::vector<FullTile> full(n);
-        std::vector<OccTile> occ_tiles(n);
+        std::vector<OccTile>& occ_tiles = occ_tiles_;
+        occ_tiles.assign(n, OccTile{});
+        last_seam_blk_.clear();
         std::vector<ImageDev> idev(n);
         size_t occ_bytes = 0;
         int max_w = 0, max_h = 0;
@@ -816,8 +838,6 @@ void Composer::plan(const isb_camera* cams, const int* sizes_wh, int n, int* cor
             ISB_CUDA(cudaMemsetAsync(need_dev_.ensure(std::max<size_t>(occ_bytes, 1) * sizeof(uint32_t)), 0,
                                      std::max<size_t>(occ_bytes, 1) * sizeof(uint32_t), st));
             need_gen_ = 0;
-            occ_max_cw_ = max_w >> g.nb;
-            occ_max_ch_ = max_h >> g.nb;
             ISB_CUDA(cudaMemsetAsync(od, 0, std::max<size_t>(occ_bytes, 1), st));
             for (int z0 = 0; z0 < n; z0 += 32768)
                 launch_occupancy(otp + z0, std::min(32768, n - z0), max_w, max_h, idp, g.nb, od, st);
@@ -904,7 +924,6 @@ void Composer::run(const isb_image* imgs, const isb_gainmap* gains, const isb_ma
     std::vector<ImageDev> idev(n);
     std::vector<LinCoef> gx, gy;
     std::vector<uint32_t> mx, my;
-    int max_mw = 0, max_mh = 0;
     for (int i = 0; i < n; ++i) {
         ImageDev& I = idev[i];
         I = ImageDev{};
@@ -974,8 +993,6 @@ void Composer::run(const isb_image* imgs, const isb_gainmap* gains, const isb_ma
                 I.seam_raw = reinterpret_cast<const uint8_t*>(db + sraw_off[i]);
                 I.seam_raw_pitch = m.width;
             }
-            max_mw = std::max(max_mw, m.width);
-            max_mh = std::max(max_mh, m.height);
             if (P.seam_w != m.width || P.seam_h != m.height) {
                 build_linear_exact_table(m.width, P.roi.w, mx);
                 build_linear_exact_table(m.height, P.roi.h, my);
@@ -1002,8 +1019,23 @@ void Composer::run(const isb_image* imgs, const isb_gainmap* gains, const isb_ma
     ISB_CUDA(cudaEventRecord(ev_[1], st));
     const bool cull = seams && eng_.geom().nb >= 2;
     if (cull) ++need_gen_;
-    launch_seam_prep(idp, n, max_mw, max_mh, occ_tiles_dev_.as<OccTile>(), occ_max_cw_, occ_max_ch_, eng_.geom().nb,
-                     occ_valid_dev_.as<uint8_t>(), cull ? need_dev_.as<uint32_t>() : nullptr, need_gen_, st);
+    {   // dense block lists of the seam preparation launch (see seam_prep_kernel); uploaded when they change
+        std::vector<int> blk(2 * (size_t)n + 2, 0);
+        for (int i = 0; i < n; ++i)
+            blk[i + 1] = blk[i] + (idev[i].seam ? ((idev[i].mw + 127) / 128) * ((idev[i].mh + 7) / 8) : 0);
+        blk[n + 1] = blk[n];
+        for (int i = 0; i < n; ++i) {
+            const int cw = occ_tiles_[i].w >> eng_.geom().nb, ch = occ_tiles_[i].h >> eng_.geom().nb;
+            blk[n + 2 + i] = blk[n + 1 + i] + (cull ? ((cw + 31) / 32) * ((ch + 7) / 8) : 0);
+        }
+        int* bd = static_cast<int*>(seam_blk_dev_.ensure(blk.size() * sizeof(int)));
+        if (blk != last_seam_blk_) {
+            ISB_CUDA(cudaMemcpyAsync(bd, blk.data(), blk.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+            last_seam_blk_ = blk;
+        }
+        launch_seam_prep(idp, n, bd, blk.back(), occ_tiles_dev_.as<OccTile>(), eng_.geom().nb, occ_valid_dev_.as<uint8_t>(),
+                         need_dev_.as<uint32_t>(), need_gen_, st);
+    }
     launch_warp_tiles_packed(eng_.warp_work_dev(), (int)eng_.warp_work().size(), eng_.tiles_dev(), idp, eng_.geom().nb, need_gen_, st);
     // ---- stage 2: pyramids (kernel 2) ---------------------------------------------------------
     ISB_CUDA(cudaEventRecord(ev_[2], st));

@@ -120,7 +120,7 @@ private:
     int committed_ = 0;           // tiles [0, committed_) have storage
     Arena arena_;                 // fused path: one block for all tiles
     std::vector<DevBuf*> extra_;  // classic path: one allocation per late-added tile
-    DevBuf tiles_dev_, warp_work_dev_, down_work_dev_, cells_dev_, dst_buf_, tmaps_dev_;
+    DevBuf tiles_dev_, warp_work_dev_, down_work_dev_, cells_dev_, cdesc_dev_, dst_buf_, tmaps_dev_;
     bool last_fast_ = false;
     bool use_tma_ = false;  // level 0 -> 1 pyrDown staged by TMA (packed tiles large enough for a full box)
     std::vector<WorkItem> warp_work_;
@@ -250,8 +250,9 @@ private:
     Arena dyn_;                 // per-run uploads: sources, gains, seam masks, their coefficient tables
     DevBuf imgs_dev_, counts_dev_, out8_, outm_, out16_;
     // seam-aware culling: plan-time valid occupancy per macro cell (device), per-run map of needed cells
-    DevBuf occ_valid_dev_, need_dev_, occ_tiles_dev_;
-    int occ_max_cw_ = 0, occ_max_ch_ = 0;
+    DevBuf occ_valid_dev_, need_dev_, occ_tiles_dev_, seam_blk_dev_;
+    std::vector<OccTile> occ_tiles_;      // one per image: its full feed() tile on the 2^nb grid
+    std::vector<int> last_seam_blk_;      // block prefix sums of the seam preparation launch as last uploaded
     uint32_t need_gen_ = 0;  // run counter stamped into the need map
     std::vector<unsigned long long> valid_counts_;
     cudaEvent_t ev_[8] = {};

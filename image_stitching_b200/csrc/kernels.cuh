@@ -85,11 +85,13 @@ void launch_occupancy(const OccTile* tiles_dev, int n_tiles, int max_w, int max_
 void launch_warp_tiles_packed(const WorkItem* work, int n_work, const TileDev* tiles, const ImageDev* imgs, int nb, uint32_t gen,
                               cudaStream_t st);
 // per-run seam preparation in one launch: (1) cv::dilate(3x3) of every image's seam mask, imgs[i].seam_raw -> imgs[i].seam;
-// (2) seam-aware culling (need != nullptr): every macro cell that holds a valid pixel (plan-time occupancy) and in which the
-// upsampled dilated seam mask can be non-zero stamps `gen` into need[] for all cells within 4 cells of it.  One OccTile per
-// image (its full feed() tile on the 2^nb grid).
-void launch_seam_prep(const ImageDev* imgs_dev, int n_img, int max_mw, int max_mh, const OccTile* tiles_dev, int max_cw, int max_ch,
-                      int nb, const uint8_t* occ_valid, uint32_t* need, uint32_t gen, cudaStream_t st);
+// (2) seam-aware culling: every macro cell that holds a valid pixel (plan-time occupancy) and in which the upsampled
+// dilated seam mask can be non-zero stamps `gen` into need[] for all cells within 4 cells of it.  One OccTile per image
+// (its full feed() tile on the 2^nb grid).  blk_dev = 2 (n_img + 1) block prefix sums: dilate blocks of 128 x 8 mask pixels
+// per image, then - continuing the count - culling blocks of 32 x 8 cells per image (none when culling is off);
+// n_blocks = the last entry.
+void launch_seam_prep(const ImageDev* imgs_dev, int n_img, const int* blk_dev, int n_blocks, const OccTile* tiles_dev, int nb,
+                      const uint8_t* occ_valid, uint32_t* need, uint32_t gen, cudaStream_t st);
 // register-rolling separable pyrDown, 2 outputs per thread (packed or planar storage)
 // odd_width: the level's output width may be odd (last level of packed tiles at least two macro cells wide)
 void launch_pyrdown_fast(const WorkItem* work, int n_work, const TileDev* tiles, int level, bool packed, int rows_per_warp,
