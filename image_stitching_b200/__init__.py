@@ -17,7 +17,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "libisb.so")
+# ISB_LIBRARY: another build of the same library (A/B of compile-time tunables, tools/ab_env.py); never a fallback
+_SO = os.environ.get("ISB_LIBRARY") or os.path.join(_HERE, "libisb.so")
 _lib = None
 
 SPHERICAL, CYLINDRICAL = 0, 1
