@@ -666,6 +666,7 @@ void Blender::feed(const int16_t* img, size_t ipitch, const uint8_t* mask, size_
     }
     launch_pack_tile(eng_.tiles_dev() + t, eng_.tiles()[t], di, (long long)dip, dm, (long long)dmp, st);
     eng_.build_pyramids(t, t + 1, st);
+    ISB_CUDA(take_launch_error());
     ISB_CUDA(cudaStreamSynchronize(st));  // feed keeps no reference to img/mask after it returns
 }
 
@@ -688,6 +689,7 @@ void Blender::blend(int16_t* dst, size_t dpitch, uint8_t* dmask, size_t mpitch)
         o.mpitch = dmk ? (long long)mpitch : rf.w;
     }
     eng_.blend(o, st);
+    ISB_CUDA(take_launch_error());
     if (dst && !d16) copy2d(dst, dpitch, o.out16, (size_t)o.pitch16, (size_t)rf.w * 6, rf.h, st);
     if (dmask && !dmk) copy2d(dmask, mpitch, o.mask, (size_t)o.mpitch, rf.w, rf.h, st);
     ISB_CUDA(cudaStreamSynchronize(st));
@@ -1076,6 +1078,7 @@ void Composer::run(const isb_image* imgs, const isb_gainmap* gains, const isb_ma
     // local ones reliably): their stores go out as staged 16-byte vectors; a single GPU is served better by direct stores
     o.peer = d8 && cfg_.strip_count > 1;
     eng_.blend(o, st);
+    ISB_CUDA(take_launch_error());  // a kernel of the chain that could not be launched must not pass as a finished run
     // ---- stage 4: results to the host ---------------------------------------------------------
     ISB_CUDA(cudaEventRecord(ev_[4], st));
     const int rows = std::max(oy1 - oy0, 0);

@@ -27,6 +27,18 @@ long long launch_count(bool reset)
 #define ISB_COUNT_LAUNCH() (++g_launches)
 void count_launch() { ++g_launches; }
 
+static thread_local cudaError_t t_launch_error = cudaSuccess;
+void note_launch_error(cudaError_t e)
+{
+    if (e != cudaSuccess && t_launch_error == cudaSuccess) t_launch_error = e;
+}
+cudaError_t take_launch_error()
+{
+    const cudaError_t e = t_launch_error;
+    t_launch_error = cudaSuccess;
+    return e;
+}
+
 bool pdl_enabled()
 {
     const char* e = getenv("ISB_PDL");  // read on every launch: a tuning switch, a few ns next to a launch

@@ -16,6 +16,9 @@ void count_launch();
 // trigger only fires once ALL CTAs of this grid have executed it) and then waits until the grid it depends on has
 // completed and flushed its memory.  Launched without the attribute (classic per-call API) both instructions are no-ops.
 bool pdl_enabled();  // ISB_PDL=0 turns the launch attribute off (A/B measurements)
+// first error a chained launch returned since the last call (cudaSuccess if none); the engine turns it into ISB_ERR_GPU_API
+void note_launch_error(cudaError_t e);
+cudaError_t take_launch_error();
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_prologue()
 {
@@ -36,7 +39,7 @@ inline void launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 block, size
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
-    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+    note_launch_error(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
     count_launch();
 }
 #endif
