@@ -68,6 +68,22 @@ def main():
     np.savez_compressed(os.path.join(OUT, "primitives.npz"), **prim)
     print("primitives written")
     simple_blenders()
+    default_flow_vectors()
+
+
+def default_flow_vectors():
+    """cfg1-substitute: the reference's default flow (tests/test_default_flow.py) through cv2."""
+    import test_default_flow as tdf
+    ref = tdf.cv2_flow(cv2)
+    out = ref["out"]
+    arrs = dict(nb=np.array(ref["nb"]), sz=np.array(ref["sz"], np.int32), rois=np.array(ref["rois"], np.int32),
+                dst_roi=np.array(out["dst_roi"], np.int32), resized0=ref["resized"][0],
+                resized_sums=np.array([int(r.astype(np.int64).sum()) for r in ref["resized"]], np.int64),
+                mask=out["mask"], result16=out["result16"], cv2_version=np.array(cv2.__version__))
+    for i, s_ in enumerate(ref["seams"]):
+        arrs[f"seam_{i}"] = s_
+    np.savez_compressed(os.path.join(OUT, "default_flow.npz"), **arrs)
+    print("default_flow", out["dst_roi"], "bands", ref["nb"])
 
 
 def simple_blend_inputs():

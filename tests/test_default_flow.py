@@ -18,6 +18,7 @@ seam_megapix = 0.1, compose_megapix = 0.4, blend_strength = 5), fed with the syn
 The reduced frames keep the megapixel RATIOS of a 12 MP camera (the scale factors are what the flow depends on).
 """
 import math
+import os
 
 import numpy as np
 import pytest
@@ -130,9 +131,8 @@ def test_reference_band_count_formula():
     assert reference_num_bands(82488, 32653) == 11
 
 
-def test_default_flow_oracle_vs_cv2(cv2_parity):
-    """CPU only: the C restatement against OpenCV on the reference's default flow (cfg1-substitute)."""
-    cv2 = cv2_parity
+def cv2_flow(cv2, **kw):
+    """The same flow through OpenCV itself (parity mode must be on: cv_reference.set_parity_mode)."""
     from oracle import cv_reference as cvr
 
     def warp_nearest(kind, s, src, K, R):
@@ -141,16 +141,37 @@ def test_default_flow_oracle_vs_cv2(cv2_parity):
     def warp_roi(kind, s, w, h, K, R):
         return tuple(int(v) for v in cvr.make_warper(kind, s).warpRoi((int(w), int(h)), K, R))
 
-    ref = default_flow(
+    return default_flow(
         rotate180=lambda a: cv2.rotate(a, cv2.ROTATE_180),
         resize_fx=lambda a, f: cv2.resize(a, None, fx=f, fy=f, interpolation=cv2.INTER_LINEAR_EXACT),
-        warp_nearest=warp_nearest, warp_roi=warp_roi, compose=cvr.compose_cv)
+        warp_nearest=warp_nearest, warp_roi=warp_roi, compose=cvr.compose_cv, **kw)
+
+
+def test_default_flow_oracle_vs_cv2(cv2_parity):
+    """CPU only: the C restatement against OpenCV on the reference's default flow (cfg1-substitute)."""
+    ref = cv2_flow(cv2_parity)
     got = oracle_flow()
     dmax, exact16 = assert_same_flow(got, ref)
     # ... and the oracle's own bar: bit-exact except for the <= 1e-4 of pixels the f32 gain-map resize can move (SURVEY.md A.7)
     n_diff = int((got["out"]["result16"] != ref["out"]["result16"]).sum())
     assert n_diff <= 1e-3 * ref["out"]["result16"].size, (n_diff, dmax)
     assert 2 <= got["nb"] <= 8
+
+
+def test_default_flow_oracle_vs_golden():
+    """The same check without cv2: tests/golden/default_flow.npz was written by tests/golden/make_golden.py from cv2 4.13.0."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "default_flow.npz"))
+    got = oracle_flow()
+    assert got["nb"] == int(g["nb"]) and got["sz"] == tuple(int(v) for v in g["sz"])
+    assert [tuple(r) for r in got["rois"]] == [tuple(int(v) for v in r) for r in g["rois"]]
+    assert tuple(got["out"]["dst_roi"]) == tuple(int(v) for v in g["dst_roi"])
+    for i, s in enumerate(got["seams"]):
+        assert np.array_equal(s, g[f"seam_{i}"])
+    assert np.array_equal(got["resized"][0], g["resized0"])
+    assert [int(r.astype(np.int64).sum()) for r in got["resized"]] == [int(v) for v in g["resized_sums"]]
+    assert np.array_equal(got["out"]["mask"], g["mask"])
+    n_diff = int((got["out"]["result16"] != g["result16"]).sum())
+    assert n_diff <= 1e-3 * g["result16"].size and np.abs(got["out"]["result16"].astype(int) - g["result16"].astype(int)).max() <= 1
 
 
 @pytest.mark.gpu
