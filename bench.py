@@ -4,16 +4,21 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2]
 
 One "step" = one pass of the compositing hot path (image_stitching.cpp:1086-1229: warp, mask, gain, ->16S,
-seam mask, MultiBandBlender prepare/feed/blend, saturate to 8U) over the synthetic cfg2 rig of SURVEY.md 8(d):
-8 x 4000x3000 images, spherical warp, 5 bands, 20912x2881 panorama.
+seam mask, MultiBandBlender prepare/feed/blend, saturate to 8U) over a synthetic rig of SURVEY.md 8(d); the default
+is cfg2: 8 x 4000x3000 images, spherical warp, 5 bands, 20912x2881 panorama.
 
-  value  : device-resident inputs -> device-resident panorama (on rank 0 when N > 1), CUDA-event timed.
-  e2e    : the same step through the C ABI with pinned HOST buffers (H2D of the sources and D2H of the
-           panorama inside the timed region).
-  N > 1  : the panorama is cut into N horizontal strips (2^nb-aligned, 4*2^nb halo rows recomputed); each
-           rank composes its strip and the strips are gathered on rank 0 over NCCL.  scaling = "strong".
-  --impl reference : the reference's own CPU implementation of the path (OpenCV's cv::detail classes, driven
-           through cv2 in the reference's call order) on the host cores; rank 0 only.
+  value  : device-resident inputs -> device-resident panorama (on rank 0 when N > 1), CUDA-event timed, max over ranks.
+  e2e    : the same step through the C ABI with pinned HOST buffers (H2D of the sources and D2H of the panorama inside
+           the timed region).  N > 1: sources and panorama live in pinned host memory shared by the ranks of the node
+           (one copy); every rank uploads the source row bands its strip reads and downloads its strip into the
+           shared panorama over its own PCIe link.
+  N > 1  : the panorama is cut into N horizontal strips (2^nb-aligned; 4 + 3 halo cells recomputed); each rank composes
+           its strip; the strips are gathered into rank 0's double-buffered panorama over NVLink - by the copy engine
+           (default, overlaps the next step), by peer stores from the final kernel (--gather p2p) or by NCCL (--gather
+           nccl).  scaling = "strong".  Every line carries `parity` (gathered panorama vs the unsharded result computed on
+           rank 0, and vs cv2) and a `cfg3` sub-record (the 36 x 24 MP rig the north star names for strip scaling).
+  --impl reference : the reference's own CPU implementation of the path (OpenCV's cv::detail classes, driven through cv2
+           in the reference's call order) on the host cores, all images of the rig per step; rank 0 only.
 """
 from __future__ import annotations
 
@@ -89,17 +94,48 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def make_inputs(workload, div=1):
+# ---------------------------------------------------------------------------------------------------------------------
+# inputs
+# ---------------------------------------------------------------------------------------------------------------------
+def make_inputs(workload, div=1, images=True):
+    from concurrent.futures import ThreadPoolExecutor
+
     from image_stitching_b200 import synth
     rig = synth.make_rig(workload, scale_div=div)
-    imgs = [synth.make_image(i, rig.W, rig.H) for i in range(rig.n)]
-    gains = synth.make_gains(rig.n)
-    return rig, imgs, gains
+    imgs = None
+    if images:
+        with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:  # numpy releases the GIL in the big ops
+            imgs = list(ex.map(lambda i: synth.make_image(i, rig.W, rig.H), range(rig.n)))
+    return rig, imgs, synth.make_gains(rig.n)
 
 
-def synth_image(index, rig):
-    from image_stitching_b200 import synth
-    return synth.make_image(index, rig.W, rig.H)
+def torch_images(rig, dev, seed0=1000):
+    """Device-generated stand-ins of synth.make_image (same construction: x32 bilinear field + noise in [-10, 10]) for
+    workloads whose numpy generation would take minutes (cfg3: 36 x 24 MP).  Only used where the checker is the CUDA
+    path itself on the same inputs (strips vs unsharded); oracle / cv2 parity runs use the numpy images."""
+    import torch
+    out = []
+    for i in range(rig.n):
+        g = torch.Generator(device=dev)
+        g.manual_seed(seed0 + i)
+        low = torch.randint(0, 256, (1, 3, rig.H // 32 + 2, rig.W // 32 + 2), generator=g, device=dev, dtype=torch.int32).float()
+        up = torch.nn.functional.interpolate(low, scale_factor=32, mode="bilinear", align_corners=False)[0, :, : rig.H, : rig.W]
+        up = up.permute(1, 2, 0)
+        up = up + torch.randint(-10, 11, up.shape, generator=g, device=dev, dtype=torch.int32).float()
+        out.append(up.round_().clamp_(0, 255).to(torch.uint8).contiguous())
+        del low, up
+    return out
+
+
+def workload_name(rig, name, div):
+    return (f"{name}{'' if div == 1 else '/div' + str(div)}: {rig.n}x{rig.W}x{rig.H} 8UC3, {rig.warp} warp, "
+            f"{rig.nb}-band multi-band blend")
+
+
+def config_of(rig, name, div, roi):
+    """The `config` both arms print - identical dicts, so the driver can tell that they ran the same thing."""
+    return {"workload": workload_name(rig, name, div), "panorama": [int(roi[2]), int(roi[3])],
+            "output_MP": roi[2] * roi[3] / 1e6, "images_per_step": rig.n}
 
 
 def seam_masks_gpu(rig):
@@ -114,60 +150,475 @@ def seam_masks_gpu(rig):
     return out
 
 
-def cpu_reference_step(rig, imgs, gains, seams, n_images=None, timings=None):
-    """One pass of the reference CPU path on the first n_images of the rig; returns (seconds, output MP, result)."""
+def cpu_reference_step(rig, imgs, gains, seams, timings=None):
+    """One pass of the reference CPU path over ALL images of the rig; returns (seconds, output MP, result)."""
     from oracle import cv_reference as cvr
-    n = rig.n if n_images is None else n_images
     t0 = time.perf_counter()
-    ref = cvr.compose_cv(imgs[:n], rig.Ks[:n], rig.Rs[:n], rig.scale, rig.warp, rig.nb, gains[:n],
-                         None if seams is None else seams[:n], timings=timings)
+    ref = cvr.compose_cv(imgs, rig.Ks, rig.Rs, rig.scale, rig.warp, rig.nb, gains, seams, timings=timings)
     dt = time.perf_counter() - t0
     return dt, ref["dst_roi"][2] * ref["dst_roi"][3] / 1e6, ref
 
 
-def seam_masks_cpu(rig):
-    from oracle import cv_reference as cvr
-    return cvr.seam_masks_cv(rig.warp, rig.scale, rig.Ks, rig.Rs, rig.W, rig.H)
-
-
+# ---------------------------------------------------------------------------------------------------------------------
+# reference arm
+# ---------------------------------------------------------------------------------------------------------------------
 def run_reference(args, rank, world):
     if rank != 0:
         return
     import cv2
     from oracle import cv_reference as cvr
-    cv2.ipp.setUseIPP(True)  # timing: the wheel as shipped
     cv2.ocl.setUseOpenCL(False)
+    # IPP OFF in both CPU legs (this arm and the `cpu_baseline` pass of our arm): the reference's vcpkg build has no `ipp`
+    # feature (vcpkg.json:6-9) and it is the setting in which the wheel is bit-exact with the restatement
+    cv2.ipp.setUseIPP(False)
     rig, imgs, gains = make_inputs(args.workload, args.div)
-    seams = seam_masks_cpu(rig)
-    # bounded sample: as many leading images of the rig as fit a ~150 s budget for the whole K+W run
-    t1, _, _ = cpu_reference_step(rig, imgs, gains, seams, n_images=1)
-    budget = 150.0 / max(1, args.steps + args.warmup)
-    n_s = int(max(1, min(rig.n, budget // max(t1, 1e-3))))
+    seams = cvr.seam_masks_cv(rig.warp, rig.scale, rig.Ks, rig.Rs, rig.W, rig.H)
+    steps = args.steps if args.steps is not None else 10
     for _ in range(args.warmup):
-        cpu_reference_step(rig, imgs, gains, seams, n_images=n_s)
-    tot, mp = 0.0, 0.0
-    for _ in range(args.steps):
-        dt, m, _ = cpu_reference_step(rig, imgs, gains, seams, n_images=n_s)
+        cpu_reference_step(rig, imgs, gains, seams)
+    tot, mp, roi = 0.0, 0.0, None
+    for _ in range(steps):
+        dt, m, ref = cpu_reference_step(rig, imgs, gains, seams)
         tot += dt
         mp += m
+        roi = ref["dst_roi"]
     val = mp / tot
+    # one more pass with IPP as the wheel ships it, reported beside the headline (only the f32 gain resize changes)
+    cv2.ipp.setUseIPP(True)
+    dt_ipp, m_ipp, _ = cpu_reference_step(rig, imgs, gains, seams)
     cores = cv2.getNumThreads()
-    sample = (f"first {n_s} of {rig.n} images of {args.workload} ({rig.W}x{rig.H}, {rig.warp}, {rig.nb} bands) per step; "
-              f"OpenCV {cv2.__version__} (cv2 wheel, IPP on) cv::detail warper/compensator/MultiBandBlender in the "
-              f"reference's call order; the reference's main() needs OpenCV dev files + libexif and cannot be built here")
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * tot / max(1, args.steps), "higher_is_better": True,
+    sample = (f"all {rig.n} of {rig.n} images of {args.workload} ({rig.W}x{rig.H}, {rig.warp}, {rig.nb} bands) per step; "
+              f"OpenCV {cv2.__version__} (cv2 wheel, IPP off like the reference's vcpkg build) cv::detail warper/compensator/"
+              f"MultiBandBlender in the reference's call order; the reference's main() needs OpenCV dev files + libexif "
+              f"and cannot be built here")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * tot / max(1, steps), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "u8/s16/f32", "data": "synthetic",
-            "config": {"workload": workload_name(rig, args)},
+            "config": config_of(rig, args.workload, args.div, roi),
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": int(cores), "kind": "reference", "sample": sample,
-                             "host_cpus": os.cpu_count()},
+                             "host_cpus": os.cpu_count(), "ipp": False, "value_with_ipp_on": m_ipp / dt_ipp},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def workload_name(rig, args):
-    return (f"{args.workload}{'' if args.div == 1 else '/div' + str(args.div)}: {rig.n}x{rig.W}x{rig.H} 8UC3, {rig.warp} warp, "
-            f"{rig.nb}-band multi-band blend")
+# ---------------------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------------------
+class SharedPinned:
+    """Pinned host memory shared by the ranks of one node (POSIX shared memory + cudaHostRegister): the host-side home of
+    the sources and of the panorama in the N > 1 end-to-end measurement."""
+
+    def __init__(self, nbytes, rank, world, tag):
+        import torch
+        import torch.distributed as dist
+        from multiprocessing import resource_tracker, shared_memory
+        self.nbytes = int(nbytes)
+        name = [None]
+        if rank == 0:
+            self.shm = shared_memory.SharedMemory(create=True, size=self.nbytes)
+            name[0] = self.shm.name
+        if world > 1:
+            dist.broadcast_object_list(name, src=0)
+        if rank != 0:
+            self.shm = shared_memory.SharedMemory(name=name[0])
+            try:  # the creator unlinks; attached processes must not (python < 3.13 registers them with the tracker)
+                resource_tracker.unregister(self.shm._name, "shared_memory")
+            except Exception:
+                pass
+        self.rank = rank
+        self.arr = np.ndarray((self.nbytes,), np.uint8, buffer=self.shm.buf)
+        self.registered = False
+        rc = torch.cuda.cudart().cudaHostRegister(self.arr.ctypes.data, self.nbytes, 0)
+        if int(rc) != 0:
+            raise RuntimeError(f"cudaHostRegister failed ({rc})")
+        self.registered = True
+
+    def view(self, offset, shape):
+        n = int(np.prod(shape))
+        return self.arr[offset:offset + n].reshape(shape)
+
+    def close(self):
+        import torch
+        if self.registered:
+            torch.cuda.cudart().cudaHostUnregister(self.arr.ctypes.data)
+            self.registered = False
+        self.arr = None
+        try:
+            self.shm.close()
+            if self.rank == 0:
+                self.shm.unlink()
+        except Exception:
+            pass
+
+
+def measure(name, div, args, rank, world, dev, stream, full):
+    """Times one workload.  full: with e2e, clocks, CPU baseline (the headline workload); else device value + parity only."""
+    import torch
+    import torch.distributed as dist
+
+    import image_stitching_b200 as isb
+    from image_stitching_b200 import strips
+
+    local = dev.index
+    rig, imgs, gains = make_inputs(name, div, images=full)
+    seams = seam_masks_gpu(rig)
+    cams = isb.cameras_from_KR(rig.Ks, rig.Rs)
+    sizes = [(rig.W, rig.H)] * rig.n
+    mode = args.gather if world > 1 else "none"
+    gm = {"none": isb.GATHER_PEER_STORES, "p2p": isb.GATHER_PEER_STORES, "nccl": isb.GATHER_LOCAL,
+          "copy": isb.GATHER_LOCAL if rank == 0 else isb.GATHER_COPY_ENGINE}[mode]
+    depth = max(1, args.inflight)
+
+    def make_composer(d):
+        c = isb.Composer(rig.warp, rig.scale, rig.nb, strip_index=rank, strip_count=world, cache_plan=True, gather_mode=gm,
+                         pipeline_depth=d)
+        t0 = time.perf_counter()
+        geo = c.plan(cams, sizes)
+        torch.cuda.synchronize()
+        return c, geo, time.perf_counter() - t0
+
+    comp, (corners, rsizes, roi), plan_s = make_composer(depth)
+    pw, ph = roi[2], roi[3]
+    out_mp = pw * ph / 1e6
+
+    d_imgs = [torch.from_numpy(im).to(dev) for im in imgs] if imgs is not None else torch_images(rig, dev)
+    d_gains = [torch.from_numpy(g).to(dev) for g in gains]
+    d_seams = [torch.from_numpy(s).to(dev) for s in seams]
+    m_ = 1 << rig.nb  # the rigs' band counts are below the prepare() clamp, so nb is the actual band count
+    padded_h = (ph + m_ - 1) // m_ * m_
+    all_rows = strips.all_strip_rows(padded_h, ph, rig.nb, world)
+
+    # ---- the panorama(s) on rank 0 ----------------------------------------------------------------------------------
+    peer = mode in ("p2p", "copy")
+    # runs in flight (pipeline depth; copy-engine gather: step k's strips still travel while step k + 1 is composed) write
+    # to different panoramas
+    nbuf = max(depth, 2 if mode == "copy" else 1)
+    # rows padded to 128 B so that staged 16-byte stores / full-sector copies apply over NVLink
+    p8, pm = (pw * 3, pw) if not peer else ((pw * 3 + 127) // 128 * 128, (pw + 127) // 128 * 128)
+    panos = []
+    if peer:
+        ok = 1
+        handles = [None] * (2 * nbuf)
+        try:
+            if rank == 0:
+                for _ in range(nbuf):
+                    panos.append((isb.DevPtr.alloc((ph, p8)), isb.DevPtr.alloc((ph, pm))))
+                handles = [h for a, b in panos for h in (a.ipc_handle(), b.ipc_handle())]
+        except Exception as e:  # noqa: BLE001
+            ok = 0
+            sys.stderr.write(f"rank {rank}: peer-memory export failed ({e}); falling back to NCCL gather\n")
+        dist.broadcast_object_list(handles, src=0)
+        if rank != 0:
+            try:
+                for k in range(nbuf):
+                    panos.append((isb.DevPtr.open_ipc(handles[2 * k], (ph, p8)), isb.DevPtr.open_ipc(handles[2 * k + 1], (ph, pm))))
+            except Exception as e:  # noqa: BLE001
+                ok = 0
+                sys.stderr.write(f"rank {rank}: peer-memory import failed ({e}); falling back to NCCL gather\n")
+        flag = torch.tensor([ok], device=dev, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if not bool(flag.item()):  # every rank takes the same path
+            peer, mode, panos, gm = False, "nccl", [], isb.GATHER_LOCAL
+            comp, _, _ = make_composer(depth)
+    if mode == "nccl":
+        depth, nbuf = 1, 1  # the NCCL gather is ordered on the caller's stream: one run at a time
+        comp, _, _ = make_composer(1)
+    if not peer:
+        p8, pm = pw * 3, pw
+        panos = [(torch.zeros((ph, pw, 3), dtype=torch.uint8, device=dev), torch.zeros((ph, pw), dtype=torch.uint8, device=dev))
+                 for _ in range(nbuf)]
+    counter = [0]
+    active = [comp]
+
+    def step_device():
+        d_out, d_mask = panos[counter[0] % nbuf]
+        counter[0] += 1
+        active[0].run(d_imgs, d_gains, d_seams, out=d_out, out_mask=d_mask, out_pitch=p8, mask_pitch=pm)
+        if mode == "nccl":  # strips -> rank 0 over NCCL (full-width rows are contiguous slices of the panorama tensors)
+            strips.gather_strips([d_out, d_mask], all_rows, rank, world)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, join=None):
+        for _ in range(warmup):
+            fn()
+        if join:
+            join()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        if join:
+            join()  # stream-ordered: e1 fires after this rank's last strip has landed in rank 0's panorama
+        e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # join: stream-ordered wait for the runs in flight (and, with the copy-engine gather, for this rank's strips to have
+    # landed in rank 0's panorama) - the closing event of the timed region is recorded behind it
+    steps = args.steps if full else max(5, min(args.steps, 20))
+    isb.launch_count(reset=True)
+    with ClockSampler(local) as clk:
+        ms_total = timed(step_device, steps, args.warmup, comp.join)
+    launches_per_step = isb.launch_count() // max(1, steps + args.warmup)
+    ms_step = ms_total / steps
+    res = {"rig": rig, "roi": roi, "ms_step": ms_step, "value": out_mp * steps / (ms_total / 1e3), "steps": steps, "plan_s": plan_s,
+           "launches_per_step": int(launches_per_step), "clocks": clk.summary(), "gather": mode, "out_mp": out_mp,
+           "steps_in_flight": depth}
+    free, total = torch.cuda.mem_get_info(dev)
+    res["device_mem_used_gb"] = (total - free) / 1e9  # includes the library's own cudaMalloc blocks (not torch's)
+
+    # ---- one step at a time (pipeline depth 1): latency of a step, per-stage device time ------------------------------
+    if depth > 1:
+        comp.sync()
+        active[0] = None
+        del comp
+        comp, _, _ = make_composer(1)
+        active[0] = comp
+        res["latency_ms_per_step"] = timed(step_device, max(5, steps // 2), 3, comp.join) / max(5, steps // 2)
+    else:
+        res["latency_ms_per_step"] = ms_step
+    stage = {}
+    for _ in range(3):
+        step_device()
+        for k, v in comp.timings().items():
+            stage[k] = stage.get(k, 0.0) + v / 3
+    comp.sync()
+    res["stages_ms"] = stage
+
+    # ---- parity ------------------------------------------------------------------------------------------------------
+    # N > 1: the gathered panorama on rank 0 against the UNSHARDED result computed on rank 0 from the same inputs
+    counter[0] = 0
+    step_device()
+    comp.sync()
+    barrier()
+    o8 = om = None
+    parity = {}
+    if rank == 0:
+        d_out, d_mask = panos[0]
+        if peer:
+            o8 = d_out.to_numpy()[:, : pw * 3].reshape(ph, pw, 3)
+            om = d_mask.to_numpy()[:, :pw]
+        else:
+            o8, om = d_out.cpu().numpy(), d_mask.cpu().numpy()
+        if world > 1:
+            c1 = isb.Composer(rig.warp, rig.scale, rig.nb, cache_plan=True)
+            c1.plan(cams, sizes)
+            u8 = torch.zeros((ph, pw, 3), dtype=torch.uint8, device=dev)
+            um = torch.zeros((ph, pw), dtype=torch.uint8, device=dev)
+            c1.run(d_imgs, d_gains, d_seams, out=u8, out_mask=um)
+            torch.cuda.synchronize()
+            d = (torch.from_numpy(o8).to(dev).to(torch.int16) - u8.to(torch.int16)).abs()
+            parity["vs_unsharded_same_rank"] = {"max_abs_diff_8bit": int(d.max().item()), "n_diff": int((d > 0).sum().item()),
+                                                "mask_equal": bool(torch.equal(torch.from_numpy(om).to(dev), um))}
+            res["byte_model"] = c1.byte_model()
+            del c1, u8, um, d
+        else:
+            res["byte_model"] = comp.byte_model()
+    if world > 1:
+        dist.barrier()
+
+    # ---- CPU baseline (reference CPU path, one full pass) = full-size parity vs cv2 -----------------------------------
+    cpu = None
+    if rank == 0 and full and not args.no_cpu_baseline:
+        import cv2
+        cv2.ipp.setUseIPP(False)  # same setting as the reference arm; bit-exact mode of the wheel
+        cv2.ocl.setUseOpenCL(False)
+        tm = {}
+        dt, mp, ref = cpu_reference_step(rig, imgs, gains, seams, timings=tm)
+        d = np.abs(o8.astype(np.int16) - ref["result8"].astype(np.int16))
+        mse = float((d.astype(np.float64) ** 2).mean())
+        parity.update({"vs": f"cv2 {cv2.__version__} CPU path, full {name}", "max_abs_diff_8bit": int(d.max()),
+                       "n_diff": int((d > 0).sum()), "psnr_db": 99.0 if mse == 0 else float(10 * np.log10(255 ** 2 / mse)),
+                       "mask_equal": bool(np.array_equal(om, ref["mask"])),
+                       "geometry_equal": bool(ref["corners"] == corners and ref["sizes"] == rsizes
+                                              and tuple(ref["dst_roi"]) == tuple(roi))})
+        cpu = {"value": mp / dt, "unit": UNIT, "cores": int(cv2.getNumThreads()), "kind": "reference",
+               "sample": f"one full pass of {name} (all {rig.n} images) through OpenCV {cv2.__version__} "
+                         f"(cv2, IPP off) in the reference's call order, {dt:.1f} s",
+               "host_cpus": os.cpu_count(), "ipp": False, "stages_s": {k: round(v, 3) for k, v in tm.items()}}
+        del ref, d
+    if world > 1:
+        dist.barrier()
+    res["parity"] = parity or None
+    res["cpu_baseline"] = cpu
+
+    # ---- video-rate loop (BASELINE config 4): one synchronised call per frame -> latency percentiles ------------------
+    if full and args.video > 0 and world == 1:
+        from image_stitching_b200 import synth
+        sets = [d_imgs] + [[torch.from_numpy(synth.make_image(1000 * (k + 1) + i, rig.W, rig.H)).to(dev) for i in range(rig.n)]
+                           for k in range(2)]
+        lat = []
+        d_out, d_mask = panos[0]
+        for f in range(args.video + 5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            comp.run(sets[f % 3], d_gains, d_seams, out=d_out, out_mask=d_mask, out_pitch=p8, mask_pitch=pm)
+            e1.record(stream)
+            e1.synchronize()
+            if f >= 5:
+                lat.append(e0.elapsed_time(e1))
+        lat = np.array(lat)
+        res["video"] = {"frames": int(args.video), "p50_ms": float(np.percentile(lat, 50)), "p95_ms": float(np.percentile(lat, 95)),
+                        "max_ms": float(lat.max()), "fps": float(1e3 / lat.mean()), "MP_per_s": float(out_mp * 1e3 / lat.mean()),
+                        "cached": "plan (ROIs, trig tables, tile lists); weight pyramids are rebuilt every frame"}
+        del sets
+
+    # ---- e2e: pinned host buffers through the C ABI -------------------------------------------------------------------
+    if full and not args.no_e2e:
+        res["e2e"] = measure_e2e(rig, imgs, gains, seams, cams, sizes, roi, args, rank, world, dev, stream, o8, om, barrier)
+    del d_imgs, panos
+    return res
+
+
+def measure_e2e(rig, imgs, gains, seams, cams, sizes, roi, args, rank, world, dev, stream, o8_ref, om_ref, barrier):
+    """Host -> host through the C ABI.  `depth` composers in async mode on `depth` streams per rank (a double/triple-buffered
+    serving loop): step k's upload overlaps step k-1's download on the full-duplex PCIe link.  Every step uploads its inputs
+    from pinned host memory and downloads its panorama rows into pinned host memory."""
+    import torch
+    import torch.distributed as dist
+
+    import image_stitching_b200 as isb
+    pw, ph = roi[2], roi[3]
+    depth = max(1, args.e2e_depth)
+    src_bytes = rig.n * rig.W * rig.H * 3
+    out_bytes = ph * pw * 4
+    shared = None
+    if world > 1:
+        try:
+            shared = SharedPinned(src_bytes + depth * out_bytes, rank, world, "e2e")
+        except Exception as e:  # noqa: BLE001
+            sys.stderr.write(f"rank {rank}: shared pinned host memory unavailable ({e})\n")
+            shared = None
+        ok = torch.tensor([1 if shared is not None else 0], device=dev, dtype=torch.int32)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if not bool(ok.item()):
+            if shared is not None:
+                shared.close()
+            return {"unavailable": "shared pinned host memory could not be set up on this node"}
+    if shared is not None:
+        h_imgs = [shared.view(i * rig.W * rig.H * 3, (rig.H, rig.W, 3)) for i in range(rig.n)]
+        if rank == 0:
+            for d, s in zip(h_imgs, imgs):
+                d[...] = s
+        outs = [(shared.view(src_bytes + k * out_bytes, (ph, pw, 3)), shared.view(src_bytes + k * out_bytes + ph * pw * 3, (ph, pw)))
+                for k in range(depth)]
+        dist.barrier()
+    else:
+        h_imgs = [torch.from_numpy(im).pin_memory().numpy() for im in imgs]
+        outs = [(torch.zeros((ph, pw, 3), dtype=torch.uint8).pin_memory().numpy(), torch.zeros((ph, pw), dtype=torch.uint8).pin_memory().numpy())
+                for _ in range(depth)]
+    h_gains = [torch.from_numpy(g).pin_memory().numpy() for g in gains]
+    h_seams = [torch.from_numpy(s_).pin_memory().numpy() for s_ in seams]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(depth)]
+    comps = []
+    for _ in range(depth):
+        c2 = isb.Composer(rig.warp, rig.scale, rig.nb, strip_index=rank, strip_count=world, cache_plan=True, async_mode=True)
+        c2.plan(cams, sizes)
+        comps.append(c2)
+    torch.cuda.synchronize()
+
+    def pipelined(steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for s_ in streams:
+            s_.wait_event(e0)
+        for k in range(steps):
+            isb.set_stream(streams[k % depth].cuda_stream)
+            comps[k % depth].run(h_imgs, h_gains, h_seams, out=outs[k % depth][0], out_mask=outs[k % depth][1])
+        for s_ in streams:
+            stream.wait_stream(s_)
+        e1.record(stream)
+        barrier()
+        isb.set_stream(stream.cuda_stream)
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def sync_one(steps):  # depth 1: one synchronous call per step, H2D -> kernels -> D2H back to back
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            comps[0].run(h_imgs, h_gains, h_seams, out=outs[0][0], out_mask=outs[0][1])
+            comps[0].sync()
+        e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    e2e_steps = max(2, min(args.steps, 50))
+    isb.set_stream(stream.cuda_stream)
+    sync_one(2)
+    ms_sync = sync_one(max(2, e2e_steps // 4))
+    sync_steps = max(2, e2e_steps // 4)
+    pipelined(2 * depth)
+    ms_pipe = pipelined(e2e_steps)
+    h2d = comps[0].last_h2d_bytes() + sum(g.nbytes for g in gains) + sum(s.nbytes for s in seams)
+    rows = comps[0].strip_rows
+    d2h = (rows[1] - rows[0]) * pw * 4
+    tot = torch.tensor([h2d, d2h], device=dev, dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    equal = None
+    if rank == 0 and o8_ref is not None:
+        equal = bool(all(np.array_equal(o[0], o8_ref) and np.array_equal(o[1], om_ref) for o in outs))
+    out_mp = pw * ph / 1e6
+    r = {"value": out_mp * e2e_steps / (ms_pipe / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(tot[0].item()),
+         "d2h_bytes_per_step": int(tot[1].item()), "ms_per_step": ms_pipe / e2e_steps, "steps": e2e_steps,
+         "sync_ms_per_step": ms_sync / sync_steps, "pipeline_depth": depth, "host_result_equals_device_result": equal,
+         "host_memory": "pinned, shared by the node's ranks (one copy of sources and panorama)" if shared is not None else "pinned",
+         "bytes_are": "summed over ranks: each rank uploads the source row bands its strip reads and downloads its strip"}
+    del comps
+    if shared is not None:
+        barrier()
+        shared.close()
+    return r
+
+
+def roofline_of(res, world, workload):
+    peak, peak_src = peaks()
+    bm = res["byte_model"]
+    rig = res["rig"]
+    P = sum(4.0 ** -l for l in range(rig.nb + 1))
+    S, M, Ap = bm["S"], bm["M"], bm["Ap"]
+    alg = {"warp": 3 * S + 10 * M, "pyrdown": 10 * M * (P - 1), "blend": 30 * P * M + 10 * P * Ap + 4 * Ap}
+    ms_step, stage = res["ms_step"], res["stages_ms"]
+    achieved = bm["B_alg"] / (ms_step / 1e3) / 1e9
+    # measured DRAM traffic (ncu dram__bytes_read + write over the step's kernels) exists for the profiled workload on one GPU
+    traffic = traffic_src = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if world == 1 and os.path.exists(tp):
+        try:
+            t = json.load(open(tp))
+            ent = t.get("workloads", {}).get(workload)
+            if ent:
+                traffic, traffic_src = ent.get("dram_bytes_per_step"), ent.get("source")
+        except Exception:
+            pass
+    r = {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s", "frac": achieved / (peak * world),
+         "peak_per_gpu": peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+         "kernel": "whole compose step: seam_prep + warp_tiles_packed + pyrdown x nb + blend x (nb+1)",
+         "algorithmic_bytes_per_step": bm["B_alg"], "S_px": S, "M_px": M, "Ap_px": Ap,
+         "note": "frac = B_alg (SURVEY 8(d): includes the reference's accumulator read-modify-write, which this output-centric "
+                 "design never performs) / step time / peak; frac_dram = bytes actually moved (ncu) / step time / peak",
+         "stages_ms": stage,
+         "stages_frac": {k: (alg[k] / (stage[k] / 1e3) / 1e9 / (peak * world) if stage.get(k) else None) for k in alg}}
+    if traffic:
+        r["achieved_dram"] = traffic / (ms_step / 1e3) / 1e9
+        r["frac_dram"] = r["achieved_dram"] / peak
+    return r
 
 
 def run_ours(args, rank, world):
@@ -183,264 +634,42 @@ def run_ours(args, rank, world):
     dev = torch.device("cuda", local)
     stream = torch.cuda.current_stream()
     isb.set_stream(stream.cuda_stream)
+    args.steps = args.steps if args.steps is not None else 50
 
-    rig, imgs, gains = make_inputs(args.workload, args.div)
-    seams = seam_masks_gpu(rig)
-    comp = isb.Composer(rig.warp, rig.scale, rig.nb, strip_index=rank, strip_count=world, cache_plan=True)
-    cams = isb.cameras_from_KR(rig.Ks, rig.Rs)
-    sizes = [(rig.W, rig.H)] * rig.n
-    corners, rsizes, roi = comp.plan(cams, sizes)
-    pw, ph = roi[2], roi[3]
-    out_mp = pw * ph / 1e6
-
-    # device-resident inputs and outputs
-    d_imgs = [torch.from_numpy(im).to(dev) for im in imgs]
-    d_gains = [torch.from_numpy(g).to(dev) for g in gains]
-    d_seams = [torch.from_numpy(s).to(dev) for s in seams]
-    from image_stitching_b200 import strips
-    m_ = 1 << rig.nb  # the rigs' band counts are below the prepare() clamp, so nb is the actual band count
-    padded_h = (ph + m_ - 1) // m_ * m_
-    all_rows = strips.all_strip_rows(padded_h, ph, rig.nb, world)
-    use_p2p = world > 1 and args.gather == "p2p"
-    # peer-memory gather: rows padded to 128 B so that the level-0 blend kernel's staged 16-byte stores apply over NVLink
-    p8, pm = (pw * 3, pw) if not use_p2p else ((pw * 3 + 127) // 128 * 128, (pw + 127) // 128 * 128)
-    if use_p2p:
-        # fused collapse + gather: rank 0 owns the panorama, the other ranks map it through CUDA IPC and their final
-        # blend kernel stores its rows straight into rank 0's HBM over NVLink (no separate collective, no staging)
-        ok = 1
-        try:
-            if rank == 0:
-                d_out, d_mask = isb.DevPtr.alloc((ph, p8)), isb.DevPtr.alloc((ph, pm))
-                handles = [d_out.ipc_handle(), d_mask.ipc_handle()]
-            else:
-                handles = [None, None]
-        except Exception as e:  # noqa: BLE001
-            handles, ok = [None, None], 0
-            sys.stderr.write(f"rank {rank}: peer-memory export failed ({e}); falling back to NCCL gather\n")
-        dist.broadcast_object_list(handles, src=0)
-        if rank != 0:
-            try:
-                d_out, d_mask = isb.DevPtr.open_ipc(handles[0], (ph, p8)), isb.DevPtr.open_ipc(handles[1], (ph, pm))
-            except Exception as e:  # noqa: BLE001
-                ok = 0
-                sys.stderr.write(f"rank {rank}: peer-memory import failed ({e}); falling back to NCCL gather\n")
-        flag = torch.tensor([ok], device=dev, dtype=torch.int32)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        use_p2p = bool(flag.item())  # every rank takes the same path
-    if not use_p2p:
-        p8, pm = pw * 3, pw
-        d_out = torch.zeros((ph, pw, 3), dtype=torch.uint8, device=dev)
-        d_mask = torch.zeros((ph, pw), dtype=torch.uint8, device=dev)
-
-    def gather_strips(rows):
-        # strips -> rank 0 over NCCL (full-width rows are contiguous slices of the panorama tensors)
-        assert tuple(rows) == tuple(all_rows[rank])
-        if not use_p2p:
-            strips.gather_strips([d_out, d_mask], all_rows, rank, world)
-
-    def step_device():
-        r = comp.run(d_imgs, d_gains, d_seams, out=d_out, out_mask=d_mask, out_pitch=p8, mask_pitch=pm)
-        if world > 1:
-            gather_strips(r["strip_rows"])
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps, warmup):
-        for _ in range(warmup):
-            fn()
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(steps):
-            fn()
-        e1.record(stream)
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
-
-    # ---- value: device-resident -------------------------------------------------------------------
-    isb.launch_count(reset=True)
-    with ClockSampler(local) as clk:
-        ms_total = timed(step_device, args.steps, args.warmup)
-    launches_per_step = isb.launch_count() // max(1, args.steps + args.warmup)
-    ms_step = ms_total / args.steps
-    value = out_mp * args.steps / (ms_total / 1e3)
-
-    video = None
-    if args.video > 0 and world == 1:
-        # BASELINE config 4 style serving loop: fixed cameras / masks / gains (plan cached), new pixels every frame
-        # (three resident frame sets cycled), one synchronised call per frame -> latency percentiles + throughput
-        sets = [d_imgs] + [[torch.from_numpy(synth_image(1000 * (k + 1) + i, rig)).to(dev) for i in range(rig.n)] for k in range(2)]
-        lat = []
-        for f in range(args.video + 5):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            comp.run(sets[f % 3], d_gains, d_seams, out=d_out, out_mask=d_mask, out_pitch=p8, mask_pitch=pm)
-            e1.record(stream)
-            e1.synchronize()
-            if f >= 5:
-                lat.append(e0.elapsed_time(e1))
-        lat = np.array(lat)
-        video = {"frames": int(args.video), "p50_ms": float(np.percentile(lat, 50)), "p95_ms": float(np.percentile(lat, 95)),
-                 "max_ms": float(lat.max()), "fps": float(1e3 / lat.mean()), "MP_per_s": float(out_mp * 1e3 / lat.mean()),
-                 "cached": "plan (ROIs, trig tables, tile lists); weight pyramids are rebuilt every frame"}
-
-    # per-stage device time (separate short loop so the event syncs do not perturb the timed region)
-    stage = {}
-    for _ in range(3):
-        comp.run(d_imgs, d_gains, d_seams, out=d_out, out_mask=d_mask, out_pitch=p8, mask_pitch=pm)
-        for k, v in comp.timings().items():
-            stage[k] = stage.get(k, 0.0) + v / 3
-
-    # ---- e2e: pinned host buffers through the C ABI ---------------------------------------------------
-    h_imgs = [torch.from_numpy(im).pin_memory() for im in imgs]
-    # (peer-memory gather: the host copies keep the padded row pitch of rank 0's panorama)
-    h_out = torch.zeros((ph, pw, 3) if p8 == pw * 3 else (ph, p8), dtype=torch.uint8).pin_memory()
-    h_mask = torch.zeros((ph, pm), dtype=torch.uint8).pin_memory()
-    h2d = sum(int(t.numel()) for t in h_imgs) + sum(g.nbytes for g in gains) + sum(s.nbytes for s in seams)
-    d2h = int(h_out.numel() + h_mask.numel()) if rank == 0 else 0
-
-    def step_e2e():
-        if world == 1:
-            comp.run([t.numpy() for t in h_imgs], gains, seams, out=h_out.numpy(), out_mask=h_mask.numpy())
-        else:
-            r = comp.run([t.numpy() for t in h_imgs], gains, seams, out=d_out, out_mask=d_mask, out_pitch=p8, mask_pitch=pm)
-            gather_strips(r["strip_rows"])
-            if use_p2p:
-                torch.cuda.synchronize()
-                dist.barrier()  # every rank's rows have landed in rank 0's panorama
-            if rank == 0:
-                if use_p2p:
-                    d_out.to_numpy(out=h_out.numpy())
-                    d_mask.to_numpy(out=h_mask.numpy())
-                else:
-                    h_out.copy_(d_out, non_blocking=True)
-                    h_mask.copy_(d_mask, non_blocking=True)
-                    torch.cuda.synchronize()
-
-    e2e_steps = max(2, min(args.steps, 50))
-    ms_e2e_sync = timed(step_e2e, e2e_steps, 2)  # one synchronous call per step: H2D -> kernels -> D2H back to back
-    e2e_extra = {"sync_ms_per_step": ms_e2e_sync / e2e_steps, "pipeline_depth": 1}
-    ms_e2e = ms_e2e_sync
-    if world == 1 and not args.no_e2e_pipeline:
-        # Same call, two composers in async_mode on two streams (a double-buffered serving loop, e.g. video-rate cfg4):
-        # step k's upload overlaps step k-1's download on the full-duplex PCIe link.  Every step still uploads its
-        # inputs from pinned host memory and downloads its panorama + mask.
-        depth = args.e2e_depth
-        streams = [torch.cuda.Stream(device=dev) for _ in range(depth)]
-        slots = []
-        for _ in range(depth):
-            c2 = isb.Composer(rig.warp, rig.scale, rig.nb, cache_plan=True, async_mode=True)
-            c2.plan(cams, sizes)
-            slots.append((c2, torch.zeros((ph, pw, 3), dtype=torch.uint8).pin_memory(),
-                          torch.zeros((ph, pw), dtype=torch.uint8).pin_memory()))
-        h_gains = [torch.from_numpy(g).pin_memory() for g in gains]
-        h_seams = [torch.from_numpy(s_).pin_memory() for s_ in seams]
-        np_imgs = [t.numpy() for t in h_imgs]
-        np_gains, np_seams = [t.numpy() for t in h_gains], [t.numpy() for t in h_seams]
-        torch.cuda.synchronize()
-
-        def pipelined(steps):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            for s_ in streams:
-                s_.wait_event(e0)
-            for k in range(steps):
-                c2, ho, hm = slots[k % depth]
-                isb.set_stream(streams[k % depth].cuda_stream)
-                c2.run(np_imgs, np_gains, np_seams, out=ho.numpy(), out_mask=hm.numpy())
-            for s_ in streams:
-                stream.wait_stream(s_)
-            e1.record(stream)
-            torch.cuda.synchronize()
-            isb.set_stream(stream.cuda_stream)
-            return e0.elapsed_time(e1)
-
-        pipelined(2 * depth)
-        ms_e2e = pipelined(e2e_steps)
-        # the async path must give the same panorama as the device-resident one
-        comp.run(d_imgs, d_gains, d_seams, out=d_out, out_mask=d_mask, out_pitch=p8, mask_pitch=pm)
-        torch.cuda.synchronize()
-        e2e_extra.update({"pipeline_depth": depth,
-                          "pipelined_equals_device_result": bool(torch.equal(slots[0][1], d_out.cpu()) and
-                                                                 torch.equal(slots[-1][2], d_mask.cpu()))})
-        del slots
-    e2e_value = out_mp * e2e_steps / (ms_e2e / 1e3)
-
-    if rank != 0:
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
-        return
-
-    # ---- roofline (SURVEY.md 8(d) byte model, whole step) ---------------------------------------------
-    peak, peak_src = peaks()
-    bm = comp.byte_model() if world == 1 else None
-    if bm is None:
-        c1 = isb.Composer(rig.warp, rig.scale, rig.nb)
-        c1.plan(cams, sizes)
-        bm = c1.byte_model()
-    P = sum(4.0 ** -l for l in range(rig.nb + 1))
-    S, M, Ap = bm["S"], bm["M"], bm["Ap"]
-    alg = {"warp": 3 * S + 10 * M, "pyrdown": 10 * M * (P - 1), "blend": 30 * P * M + 10 * P * Ap + 4 * Ap}
-    achieved = bm["B_alg"] / (ms_step / 1e3) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
-        try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_step")
-        except Exception:
-            traffic = None
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s", "frac": achieved / (peak * world),
-                "peak_per_gpu": peak,
-                "traffic": traffic, "peak_source": peak_src,
-                "kernel": "whole compose step: warp_tiles + pyrdown_tiles x nb + blend_level x (nb+1)",
-                "algorithmic_bytes_per_step": bm["B_alg"], "S_px": S, "M_px": M, "Ap_px": Ap,
-                "stages_ms": stage,
-                "stages_frac": {k: (alg[k] / (stage[k] / 1e3) / 1e9 / (peak * world) if stage.get(k) else None) for k in alg}}
-
-    # ---- CPU baseline (reference CPU path, bounded: one full pass) + full-size parity --------------------
-    cpu = None
-    parity = None
-    if not args.no_cpu_baseline and world == 1:
-        import cv2
-        cv2.ipp.setUseIPP(False)  # this pass doubles as the full-size parity check (parity mode)
-        cv2.ocl.setUseOpenCL(False)
-        tm = {}
-        dt, mp, ref = cpu_reference_step(rig, imgs, gains, seams, timings=tm)
-        ours = comp.run(d_imgs, d_gains, d_seams, out=d_out, out_mask=d_mask, out_pitch=p8, mask_pitch=pm)
-        torch.cuda.synchronize()
-        o8, om = d_out.cpu().numpy(), d_mask.cpu().numpy()
-        d = np.abs(o8.astype(np.int16) - ref["result8"].astype(np.int16))
-        mse = float((d.astype(np.float64) ** 2).mean())
-        parity = {"vs": f"cv2 {cv2.__version__} CPU path, full {args.workload}", "max_abs_diff_8bit": int(d.max()),
-                  "n_diff": int((d > 0).sum()), "psnr_db": 99.0 if mse == 0 else float(10 * np.log10(255 ** 2 / mse)),
-                  "mask_equal": bool(np.array_equal(om, ref["mask"])),
-                  "geometry_equal": bool(ref["corners"] == ours["corners"] and ref["sizes"] == ours["sizes"]
-                                         and tuple(ref["dst_roi"]) == tuple(ours["dst_roi"]))}
-        cpu = {"value": mp / dt, "unit": UNIT, "cores": int(cv2.getNumThreads()), "kind": "reference",
-               "sample": f"one full pass of {args.workload} ({rig.n} images) through OpenCV {cv2.__version__} "
-                         f"(cv2, IPP off = parity mode) in the reference's call order, {dt:.1f} s",
-               "host_cpus": os.cpu_count(), "stages_s": {k: round(v, 3) for k, v in tm.items()}}
-
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "u8/s16/f32", "data": "synthetic",
-            "config": {"workload": workload_name(rig, args), "panorama": [pw, ph], "output_MP": out_mp,
-                       "parallelism": f"strips{world}" + ("" if world == 1 else ("+p2p" if use_p2p else "+nccl") + "-gather"), "plan_cache": True,
-                       "l2": "per-step working set (sources + per-image pyramids) >> 126 MB L2; no explicit flush"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps, **e2e_extra},
-            "gpu_launches": int(launches_per_step * args.steps), "gpu_launches_per_step": int(launches_per_step),
-            "clocks": clk.summary(), "roofline": roofline, "cpu_baseline": cpu, "parity": parity}
-    if video is not None:
-        line["video"] = video
-    print(json.dumps(line), flush=True)
+    res = measure(args.workload, args.div, args, rank, world, dev, stream, full=True)
+    sub = None
+    if args.workload == "cfg2" and args.div == 1 and not args.no_cfg3:
+        # the 36 x 24 MP rig the north star names for strip scaling, in the same line at every N (device-resident value)
+        torch.cuda.empty_cache()
+        sub = measure("cfg3", 1, args, rank, world, dev, stream, full=False)
+    if rank == 0:
+        rig, roi = res["rig"], res["roi"]
+        par = f"strips{world}" + ("" if world == 1 else f"+{res['gather']}-gather")
+        line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": res["ms_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "u8/s16/f32", "data": "synthetic", "config": config_of(rig, args.workload, args.div, roi),
+                "latency_ms_per_step": res["latency_ms_per_step"],
+                "layout": {"parallelism": par, "plan_cache": True, "plan_s": res["plan_s"], "steps_in_flight": res["steps_in_flight"],
+                           "steps_in_flight_note": "ms_per_step / value are the throughput of back-to-back steps with that many "
+                                                   "runs in flight (own pyramids and panorama each); latency_ms_per_step is one "
+                                                   "step at a time",
+                           "l2": "per-step working set (sources + per-image pyramids) >> 126 MB L2; no explicit flush",
+                           "device_mem_used_gb_rank0": res["device_mem_used_gb"]},
+                "e2e": res.get("e2e"), "gpu_launches": int(res["launches_per_step"] * args.steps),
+                "gpu_launches_per_step": res["launches_per_step"], "clocks": res["clocks"],
+                "roofline": roofline_of(res, world, args.workload), "cpu_baseline": res["cpu_baseline"], "parity": res["parity"]}
+        if "video" in res:
+            line["video"] = res["video"]
+        if sub is not None:
+            rl = roofline_of(sub, world, "cfg3")
+            line["cfg3"] = {"config": config_of(sub["rig"], "cfg3", 1, sub["roi"]), "value": sub["value"], "unit": UNIT,
+                            "ms_per_step": sub["ms_step"], "latency_ms_per_step": sub["latency_ms_per_step"], "steps": sub["steps"],
+                            "steps_in_flight": sub["steps_in_flight"], "parallelism": f"strips{world}" + ("" if world == 1 else f"+{sub['gather']}-gather"),
+                            "roofline_frac": rl["frac"], "algorithmic_bytes_per_step": rl["algorithmic_bytes_per_step"],
+                            "stages_ms": sub["stages_ms"], "parity": sub["parity"], "plan_s": sub["plan_s"],
+                            "device_mem_used_gb_rank0": sub["device_mem_used_gb"],
+                            "data": "synthetic, generated on the device (same construction as the numpy rig)"}
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -449,17 +678,20 @@ def run_ours(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default 50; reference arm: 10)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--div", type=int, default=1, help="linear down-scale of the rig (dev only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cfg3", action="store_true", help="skip the cfg3 sub-record of the default (cfg2) line")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--inflight", type=int, default=3, help="runs in flight in the device-resident throughput loop (isb_config.pipeline_depth)")
     ap.add_argument("--video", type=int, default=0, help="also run N frames one call at a time and report p50/p95 latency")
-    ap.add_argument("--no-e2e-pipeline", action="store_true", help="report the synchronous one-call-per-step e2e only")
-    ap.add_argument("--e2e-depth", type=int, default=3, help="composers in flight in the pipelined e2e measurement")
-    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
-                    help="N > 1: final kernel stores into rank 0's panorama over NVLink peer memory (p2p) or NCCL send/recv")
+    ap.add_argument("--e2e-depth", type=int, default=3, help="composers in flight per rank in the pipelined e2e measurement")
+    ap.add_argument("--gather", default="copy", choices=["copy", "p2p", "nccl"],
+                    help="N > 1: strips reach rank 0's panorama by the copy engine from a local staging block (copy), by peer "
+                         "stores of the final kernel (p2p), or by NCCL send/recv (nccl)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", 0))

@@ -68,7 +68,7 @@ class _Mask(C.Structure):
 class Config(C.Structure):
     _fields_ = [("warp_kind", C.c_int), ("warped_image_scale", C.c_float), ("num_bands", C.c_int),
                 ("strip_index", C.c_int), ("strip_count", C.c_int), ("cache_plan", C.c_int), ("async_mode", C.c_int),
-                ("reserved", C.c_int * 7)]
+                ("gather_mode", C.c_int), ("pipeline_depth", C.c_int), ("reserved", C.c_int * 5)]
 
 
 class _Pano(C.Structure):
@@ -82,13 +82,23 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(_SO):
+    if "ISB_LIBRARY" not in os.environ:
         from . import build as _build
-        _build.build()
+        if not _build.up_to_date():
+            # sources newer than the binary (or no binary): rebuild when a compiler is here, never run a stale library silently
+            try:
+                _build.build()
+            except RuntimeError:
+                if not os.path.exists(_SO):
+                    raise
+                import warnings
+                warnings.warn("libisb.so is older than csrc/ and nvcc is not available to rebuild it")
     L = C.CDLL(_SO)
     L.isb_last_error.restype = C.c_char_p
     L.isb_version.restype = C.c_char_p
     L.isb_launch_count.restype = C.c_longlong
+    L.isb_composer_last_h2d_bytes.restype = C.c_longlong
+    L.isb_composer_last_h2d_bytes.argtypes = [C.c_void_p]
     L.isb_composer_stage_name.restype = C.c_char_p
     L.isb_warper_get_scale.restype = C.c_float
     for f in ("isb_warper_create", "isb_compensator_create", "isb_blender_create", "isb_composer_create",
@@ -669,11 +679,14 @@ def cameras_from_KR(Ks, Rs):
     return cams
 
 
+GATHER_PEER_STORES, GATHER_COPY_ENGINE, GATHER_LOCAL = 0, 1, 2
+
+
 class Composer:
     """The whole compositing loop on the GPU (isb_composer_*)."""
 
     def __init__(self, warp="spherical", scale=1.0, num_bands=5, strip_index=0, strip_count=1, cache_plan=True,
-                 async_mode=False):
+                 async_mode=False, gather_copy=False, gather_mode=None, pipeline_depth=1):
         self.cfg = Config()
         self.cfg.warp_kind = _KIND[warp]
         self.cfg.warped_image_scale = float(scale)
@@ -681,6 +694,9 @@ class Composer:
         self.cfg.strip_index, self.cfg.strip_count = int(strip_index), int(strip_count)
         self.cfg.cache_plan = int(bool(cache_plan))
         self.cfg.async_mode = int(bool(async_mode))
+        # GATHER_PEER_STORES (0) / GATHER_COPY_ENGINE (1) / GATHER_LOCAL (2); gather_copy=True is shorthand for 1
+        self.cfg.gather_mode = int(gather_mode) if gather_mode is not None else (GATHER_COPY_ENGINE if gather_copy else GATHER_PEER_STORES)
+        self.cfg.pipeline_depth = int(pipeline_depth)
         self._h = C.c_void_p(lib().isb_composer_create(C.byref(self.cfg)))
         self.n = 0
 
@@ -760,12 +776,25 @@ class Composer:
     def sync(self):
         _chk(lib().isb_composer_sync(self._h))
 
+    def join(self):
+        """Stream-ordered wait (no host sync) for the copy-engine gather of all previous runs."""
+        _chk(lib().isb_composer_join(self._h))
+
     def timings(self):
         ms = (C.c_float * 8)()
         n = lib().isb_composer_last_timings(self._h, ms, 8)
         if n < 0:
             _chk(n)
         return {lib().isb_composer_stage_name(i).decode(): float(ms[i]) for i in range(n)}
+
+    def source_band(self, index):
+        """Rows [lo, hi] of source image `index` this strip reads (strip-sharded plans; the whole image otherwise)."""
+        lo, hi = C.c_int(0), C.c_int(0)
+        _chk(lib().isb_composer_source_band(self._h, int(index), C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
+    def last_h2d_bytes(self):
+        return int(lib().isb_composer_last_h2d_bytes(self._h))
 
     def byte_model(self):
         S, M, A, B = C.c_double(0), C.c_double(0), C.c_double(0), C.c_double(0)

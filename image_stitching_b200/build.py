@@ -27,12 +27,24 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found: libisb.so cannot be built (there is no CPU fallback)")
 
 
+STAMP = SO + ".stamp"  # hash of the sources the binary was built from (file times do not survive a copy to the GPU box)
+
+
+def source_hash() -> str:
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted(SOURCES + HEADERS):
+        with open(os.path.join(CSRC, f), "rb") as fh:
+            h.update(f.encode() + b"\0" + fh.read())
+    h.update(os.environ.get("ISB_NVCC_FLAGS", "").encode())
+    return h.hexdigest()
+
+
 def up_to_date() -> bool:
-    if not os.path.exists(SO):
+    if not (os.path.exists(SO) and os.path.exists(STAMP)):
         return False
-    t = os.path.getmtime(SO)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
-    return all(os.path.getmtime(d) <= t for d in deps)
+    with open(STAMP) as fh:
+        return fh.read().strip() == source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -65,6 +77,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("libisb.so build failed")
     link = [_nvcc(), "-shared", "-o", SO] + objs + ["-cudart", "static", "-lpthread"]
     subprocess.check_call(link)
+    with open(STAMP, "w") as fh:
+        fh.write(source_hash() + "\n")
     return SO
 
 

@@ -16,7 +16,7 @@ struct isb_compensator { Compensator impl; isb_compensator(int w, int h) : impl(
 struct isb_blender { Blender impl; explicit isb_blender(int nb) : impl(nb) {} };
 struct isb_simple_blender { SimpleBlender impl; isb_simple_blender(int t, float s) : impl(t, s) {} };
 struct isb_timelapser { Timelapser impl; explicit isb_timelapser(int t) : impl(t) {} };
-struct isb_composer { Composer impl; explicit isb_composer(const isb_config& c) : impl(c) {} };
+struct isb_composer { ComposerPool impl; explicit isb_composer(const isb_config& c) : impl(c) {} };
 
 static thread_local std::string t_error;
 
@@ -445,17 +445,32 @@ int isb_composer_sync(isb_composer* c)
 {
     return guarded([&] { NOT_NULL(c); c->impl.sync(); });
 }
+int isb_composer_join(isb_composer* c)
+{
+    return guarded([&] { NOT_NULL(c); c->impl.join(); });
+}
 int isb_composer_last_timings(isb_composer* c, float* ms, int cap)
 {
     int n = 0;
-    const int rc = guarded([&] { NOT_NULL(c); n = c->impl.timings(ms, cap); });
+    const int rc = guarded([&] { NOT_NULL(c); n = c->impl.last().timings(ms, cap); });
     return rc == ISB_OK ? n : rc;
 }
 const char* isb_composer_stage_name(int stage) { return Composer::stage_name(stage); }
 int isb_composer_byte_model(isb_composer* c, double* S, double* M, double* Ap, double* B)
 {
-    return guarded([&] { NOT_NULL(c); c->impl.byte_model(S, M, Ap, B); });
+    return guarded([&] { NOT_NULL(c); c->impl.first().byte_model(S, M, Ap, B); });
 }
+int isb_composer_source_band(isb_composer* c, int index, int* lo, int* hi)
+{
+    return guarded([&] {
+        NOT_NULL(c);
+        const std::vector<int>& b = c->impl.first().src_band();
+        if (index < 0 || 2 * (size_t)index + 1 >= b.size()) throw Error(ISB_ERR_OUT_OF_RANGE, "image index out of range (plan first)");
+        if (lo) *lo = b[2 * index];
+        if (hi) *hi = b[2 * index + 1];
+    });
+}
+long long isb_composer_last_h2d_bytes(isb_composer* c) { return c ? (long long)c->impl.last().last_h2d_bytes() : 0; }
 int isb_compose(const isb_image* imgs, const isb_camera* cams, const isb_gainmap* gains, const isb_mask* seams, int n,
                 const isb_config* cfg, isb_pano* out)
 {

@@ -17,6 +17,8 @@ struct ImageDev {
     long long spitch;     // bytes
     unsigned sbytes;      // spitch * sh when the vectorised sampler may be used (8-B aligned base, < 4 GB), else 0
     int fast_h;           // rows y0 in [0, fast_h) whose two 16-byte tap windows stay inside the buffer for every x0 <= sw - 2
+    int band_lo;          // first source row present behind `src` (strip-sharded runs upload a row band of host sources; `src`
+                          // is then the address row 0 WOULD have, and only rows the plan-time band covers are ever read)
     int sw, sh;           // source size
     int roi_w, roi_h;     // warped size (warpRoi)
     float kr[9];          // k_rinv = K * R^T

@@ -121,6 +121,10 @@ void PyramidEngine::reset(const BlendGeometry& g, int sub_y0, int sub_h, int own
     tiles_.clear();
     committed_ = 0;
     arena_.begin();
+    // classic feed() path: the per-tile allocations of the previous prepare/feed/blend cycle (cudaFree synchronises with
+    // whatever may still read them)
+    for (DevBuf* b : extra_) delete b;
+    extra_.clear();
     warp_work_.clear();
     down_work_.assign(g.nb, {});
     dst_.cell_start = nullptr;
@@ -710,6 +714,14 @@ Composer::~Composer()
 {
     if (ev_init_)
         for (auto& e : ev_) cudaEventDestroy(e);
+    if (copy_stream_) {
+        cudaStreamSynchronize(copy_stream_);
+        for (int k = 0; k < 2; ++k) {
+            cudaEventDestroy(ev_done_[k]);
+            cudaEventDestroy(ev_copied_[k]);
+        }
+        cudaStreamDestroy(copy_stream_);
+    }
 }
 
 bool Composer::same_plan(const isb_camera* cams, const int* sizes_wh, int n) const
@@ -763,11 +775,17 @@ void Composer::plan(const isb_camera* cams, const int* sizes_wh, int n, int* cor
         dst_roi_ = result_roi(cs.data(), ss.data(), n);
         BlendGeometry g;
         g.prepare(dst_roi_, cfg_.num_bands);
-        // strip: owned rows on the 2^nb grid + halo of 4 * 2^nb rows computed redundantly
+        // strip: owned rows on the 2^nb grid + halo rows computed redundantly.  With m = 2^nb and strip cuts on the m grid,
+        // output rows [y0, y1) read collapsed rows [y0 / 2^l - 2, y1 / 2^l + 1] of level l (fine rows [a, b] read coarse rows
+        // [a/2 - 1, b/2 + 1]); a level-l row q of an image pyramid reads level-0 rows [2^l q - 2 (2^l - 1), 2^l q + 2 (2^l - 1)],
+        // and the Laplacian at row q additionally level l + 1 rows q/2 - 1 .. q/2 + 1.  The extremes are reached at the top
+        // level: rows [y0 - 4 m + 2, y1 + 3 m - 2).  So the halo is FOUR cells above and THREE cells below the strip; data
+        // beyond it - and the artificial border rules at the cuts - cannot reach an owned row.
         int y0, y1;
         strip_rows(g.roi.h, g.nb, cfg_.strip_index, cfg_.strip_count, y0, y1);
-        const int halo = cfg_.strip_count > 1 ? 4 * (1 << g.nb) : 0;
-        const int sy0 = std::max(0, y0 - halo), sy1 = std::min(g.roi.h, y1 + halo);
+        const int m = 1 << g.nb;
+        const int halo_top = cfg_.strip_count > 1 ? 4 * m : 0, halo_bot = cfg_.strip_count > 1 ? 3 * m : 0;
+        const int sy0 = std::max(0, y0 - halo_top), sy1 = std::min(g.roi.h, (y1 + m - 1) / m * m + halo_bot);
         eng_.reset(g, sy0, std::max(sy1 - sy0, 0), y0, y1, /*packed=*/true);
 
         // separable trig tables (every image) + slots for the per-run coefficient tables
@@ -876,6 +894,25 @@ void Composer::plan(const isb_camera* cams, const int* sizes_wh, int n, int* cor
             }
         }
         eng_.commit_tiles(st);
+        // strip-sharded runs: the band of source rows this strip can read from every image (host sources are uploaded
+        // band-wise).  imgs_dev_ holds the plan-time descriptors (geometry only), which is all the kernel needs.
+        src_band_.assign(2 * (size_t)n, 0);
+        for (int i = 0; i < n; ++i) src_band_[2 * i + 1] = img_[i].src_h - 1;
+        if (cfg_.strip_count > 1 && !eng_.warp_work().empty()) {
+            std::vector<int> init(2 * (size_t)n);
+            for (int i = 0; i < n; ++i) { init[2 * i] = INT_MAX; init[2 * i + 1] = INT_MIN; }
+            int* bd = static_cast<int*>(band_dev_.ensure(init.size() * sizeof(int)));
+            ISB_CUDA(cudaMemcpyAsync(bd, init.data(), init.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+            launch_src_band(eng_.warp_work_dev(), (int)eng_.warp_work().size(), eng_.tiles_dev(), imgs_dev_.as<ImageDev>(), bd, st);
+            ISB_CUDA(cudaMemcpyAsync(init.data(), bd, init.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
+            ISB_CUDA(cudaStreamSynchronize(st));
+            for (int i = 0; i < n; ++i) {
+                if (init[2 * i] > init[2 * i + 1]) continue;  // image without tiles in this strip
+                // whole multiples of 8 rows keep the (virtual) base address of row 0 8-byte aligned
+                src_band_[2 * i] = std::max(0, init[2 * i]) & ~7;
+                src_band_[2 * i + 1] = std::min(img_[i].src_h - 1, init[2 * i + 1]);
+            }
+        }
         valid_counts_.clear();
         planned_ = true;
     }
@@ -903,13 +940,15 @@ void Composer::run(const isb_image* imgs, const isb_gainmap* gains, const isb_ma
     // ---- stage 0: inputs to the device -------------------------------------------------------
     ISB_CUDA(cudaEventRecord(ev_[0], st));
     dyn_.begin();
+    h2d_bytes_ = 0;
     std::vector<size_t> src_off(n, 0), gain_off(n, 0), sraw_off(n, 0), sdil_off(n, 0);
     for (int i = 0; i < n; ++i) {
         if (tiles_of_image_[i].empty()) continue;
         const isb_image& im = imgs[i];
         if (!im.data) throw Error(ISB_ERR_NULL_PTR, "image data is null");
         ISB_ASSERT(im.width == img_[i].src_w && im.height == img_[i].src_h && im.pitch >= (size_t)im.width * 3);
-        if (mem_kind(im.data) != MemKind::Device) src_off[i] = dyn_.take((size_t)im.width * 3 * im.height);
+        if (mem_kind(im.data) != MemKind::Device)  // rows [band lo, band hi] only, + one row: room for the sampler's 16-byte
+            src_off[i] = dyn_.take((size_t)im.width * 3 * (src_band_[2 * i + 1] - src_band_[2 * i] + 2) + 32);  // windows and its speculative loads
         if (gains && gains[i].data) {
             ISB_ASSERT(gains[i].width > 0 && gains[i].height > 0);
             if (mem_kind(gains[i].data) != MemKind::Device)
@@ -957,9 +996,13 @@ void Composer::run(const isb_image* imgs, const isb_gainmap* gains, const isb_ma
             I.spitch = (long long)im.pitch;
         } else {
             const size_t rb = (size_t)im.width * 3;
-            copy2d(db + src_off[i], rb, im.data, im.pitch, rb, im.height, st);
-            I.src = reinterpret_cast<const uint8_t*>(db + src_off[i]);
+            const int lo = src_band_[2 * i], hi = src_band_[2 * i + 1];
+            copy2d(db + src_off[i], rb, im.data + (size_t)lo * im.pitch, im.pitch, rb, (size_t)(hi - lo + 1), st);
+            // the address row 0 would have: rows outside [lo, hi] are never read (src_band_kernel)
+            I.src = reinterpret_cast<const uint8_t*>(db + src_off[i]) - (size_t)lo * rb;
             I.spitch = (long long)rb;
+            I.band_lo = lo;
+            h2d_bytes_ += rb * (size_t)(hi - lo + 1);
         }
         {   // the vectorised sampler reads aligned 16-byte windows: needs an 8-B aligned base and 32-bit offsets
             const unsigned long long extent = (unsigned long long)I.spitch * (I.sh - 1) + (unsigned long long)I.sw * 3;
@@ -967,6 +1010,8 @@ void Composer::run(const isb_image* imgs, const isb_gainmap* gains, const isb_ma
             // window of tap row y0 + 1 at x0 = sw - 2 ends at (y0 + 1) * pitch + 3 * (sw - 2) + 16 at most
             const long long room = (long long)I.sbytes - 16 - 3ll * (I.sw - 2);
             I.fast_h = (I.sbytes && I.sw >= 2 && room >= I.spitch) ? (int)std::min<long long>(room / I.spitch, I.sh - 1) : 0;
+            // staged host sources end in a spare row: every tap row of the band may use the vectorised sampler
+            if (I.sbytes && I.sw >= 2 && mem_kind(im.data) != MemKind::Device) I.fast_h = I.sh - 1;
         }
         if (gains && gains[i].data) {
             const isb_gainmap& g = gains[i];
@@ -1038,7 +1083,9 @@ void Composer::run(const isb_image* imgs, const isb_gainmap* gains, const isb_ma
         launch_seam_prep(idp, n, bd, blk.back(), occ_tiles_dev_.as<OccTile>(), eng_.geom().nb, occ_valid_dev_.as<uint8_t>(),
                          need_dev_.as<uint32_t>(), need_gen_, st);
     }
-    launch_warp_tiles_packed(eng_.warp_work_dev(), (int)eng_.warp_work().size(), eng_.tiles_dev(), idp, eng_.geom().nb, need_gen_, st);
+    bool banded = false;
+    for (const ImageDev& I : idev) banded = banded || I.band_lo != 0;
+    launch_warp_tiles_packed(eng_.warp_work_dev(), (int)eng_.warp_work().size(), eng_.tiles_dev(), idp, eng_.geom().nb, need_gen_, banded, st);
     // ---- stage 2: pyramids (kernel 2) ---------------------------------------------------------
     ISB_CUDA(cudaEventRecord(ev_[2], st));
     eng_.build_pyramids(0, (int)eng_.tiles().size(), st);
@@ -1076,9 +1123,41 @@ void Composer::run(const isb_image* imgs, const isb_gainmap* gains, const isb_ma
     }
     // strip-sharded runs usually write into rank 0's panorama over NVLink (peer-mapped pointers cannot be told apart from
     // local ones reliably): their stores go out as staged 16-byte vectors; a single GPU is served better by direct stores
-    o.peer = d8 && cfg_.strip_count > 1;
+    o.peer = d8 && cfg_.strip_count > 1 && cfg_.gather_mode != ISB_GATHER_LOCAL;
+    // ISB_GATHER_COPY_ENGINE: the strip is composed into a LOCAL double-buffered staging block (direct stores) and pushed into the
+    // caller's panorama - rank 0's, peer-mapped - by the copy engine on a second stream, so the transfer overlaps the next
+    // run's kernels instead of stalling this run's last kernel on NVLink back-pressure.
+    const bool gcopy = cfg_.gather_mode == ISB_GATHER_COPY_ENGINE && cfg_.strip_count > 1 && d8 && dm && !out->data16 && oy1 > oy0;
+    int slot = 0;
+    if (gcopy) {
+        if (!copy_stream_) {
+            ISB_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+            for (int k = 0; k < 2; ++k) {
+                ISB_CUDA(cudaEventCreateWithFlags(&ev_done_[k], cudaEventDisableTiming));
+                ISB_CUDA(cudaEventCreateWithFlags(&ev_copied_[k], cudaEventDisableTiming));
+            }
+        }
+        slot = (int)(run_count_ & 1);
+        if (run_count_ >= 2) ISB_CUDA(cudaStreamWaitEvent(st, ev_copied_[slot], 0));  // the slot's previous strip has left
+        const size_t rows = (size_t)(oy1 - oy0);
+        uint8_t* s8 = static_cast<uint8_t*>(strip8_[slot].ensure(out->pitch * rows));
+        uint8_t* sm = static_cast<uint8_t*>(stripm_[slot].ensure(out->mask_pitch * rows));
+        o.out8 = s8 - (long long)(oy0 - sub0) * o.pitch8;
+        o.mask = sm - (long long)(oy0 - sub0) * o.mpitch;
+        o.peer = 0;
+    }
     eng_.blend(o, st);
     ISB_CUDA(take_launch_error());  // a kernel of the chain that could not be launched must not pass as a finished run
+    if (gcopy) {
+        const size_t rows = (size_t)(oy1 - oy0);
+        ISB_CUDA(cudaEventRecord(ev_done_[slot], st));
+        ISB_CUDA(cudaStreamWaitEvent(copy_stream_, ev_done_[slot], 0));
+        copy2d(out->data + (size_t)oy0 * out->pitch, out->pitch, strip8_[slot].as<uint8_t>(), out->pitch, (size_t)rf.w * 3, rows, copy_stream_);
+        copy2d(out->mask + (size_t)oy0 * out->mask_pitch, out->mask_pitch, stripm_[slot].as<uint8_t>(), out->mask_pitch, (size_t)rf.w, rows, copy_stream_);
+        ISB_CUDA(cudaEventRecord(ev_copied_[slot], copy_stream_));
+        copies_pending_ = true;
+    }
+    ++run_count_;
     // ---- stage 4: results to the host ---------------------------------------------------------
     ISB_CUDA(cudaEventRecord(ev_[4], st));
     const int rows = std::max(oy1 - oy0, 0);
@@ -1097,9 +1176,21 @@ void Composer::run(const isb_image* imgs, const isb_gainmap* gains, const isb_ma
     if (any_host && !cfg_.async_mode) ISB_CUDA(cudaStreamSynchronize(st));
 }
 
+void Composer::join()
+{
+    if (!copies_pending_) return;
+    cudaStream_t st = current_stream();
+    for (int k = 0; k < 2; ++k)
+        if (run_count_ > (unsigned long long)k) ISB_CUDA(cudaStreamWaitEvent(st, ev_copied_[k], 0));
+}
+
 void Composer::sync()
 {
     if (ev_init_) ISB_CUDA(cudaEventSynchronize(ev_[5]));
+    if (copies_pending_) {
+        ISB_CUDA(cudaStreamSynchronize(copy_stream_));
+        copies_pending_ = false;
+    }
 }
 
 int Composer::timings(float* ms, int cap)
@@ -1113,6 +1204,91 @@ int Composer::timings(float* ms, int cap)
         if (ms && i < cap) ms[i] = v;
     }
     return ST_COUNT;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ComposerPool
+// ------------------------------------------------------------------------------------------------
+ComposerPool::ComposerPool(const isb_config& cfg)
+{
+    const int depth = std::max(1, std::min(cfg.pipeline_depth, 8));
+    isb_config c = cfg;
+    if (depth > 1) c.async_mode = 1;  // a slot never blocks the host: that is what sync() is for
+    for (int k = 0; k < depth; ++k) comps_.push_back(new Composer(c));
+    busy_.assign(depth, 0);
+}
+
+ComposerPool::~ComposerPool()
+{
+    for (size_t k = 0; k < streams_.size(); ++k) {
+        cudaStreamSynchronize(streams_[k]);
+        cudaEventDestroy(fork_[k]);
+        cudaEventDestroy(done_[k]);
+    }
+    for (Composer* c : comps_) delete c;
+    for (cudaStream_t s : streams_) cudaStreamDestroy(s);
+}
+
+void ComposerPool::plan(const isb_camera* cams, const int* sizes_wh, int n, int* corners, int* sizes, int* dst_roi)
+{
+    for (Composer* c : comps_) c->plan(cams, sizes_wh, n, corners, sizes, dst_roi);
+}
+
+void ComposerPool::run(const isb_image* imgs, const isb_gainmap* gains, const isb_mask* seams, int n, isb_pano* out)
+{
+    if (comps_.size() == 1) {
+        comps_[0]->run(imgs, gains, seams, n, out);
+        return;
+    }
+    if (streams_.empty()) {
+        require_device();
+        for (size_t k = 0; k < comps_.size(); ++k) {
+            cudaStream_t s;
+            cudaEvent_t a, b;
+            ISB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+            ISB_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+            ISB_CUDA(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+            streams_.push_back(s);
+            fork_.push_back(a);
+            done_.push_back(b);
+        }
+    }
+    const int k = (int)(next_++ % comps_.size());
+    cudaStream_t caller = current_stream();
+    // the slot starts behind everything the caller has enqueued so far (inputs produced on its stream, the plan's uploads)
+    ISB_CUDA(cudaEventRecord(fork_[k], caller));
+    ISB_CUDA(cudaStreamWaitEvent(streams_[k], fork_[k], 0));
+    set_current_stream(streams_[k]);
+    try {
+        comps_[k]->run(imgs, gains, seams, n, out);
+    } catch (...) {
+        set_current_stream(caller);
+        throw;
+    }
+    set_current_stream(caller);
+    ISB_CUDA(cudaEventRecord(done_[k], streams_[k]));
+    busy_[k] = 1;
+    last_ = k;
+}
+
+void ComposerPool::join()
+{
+    cudaStream_t caller = current_stream();
+    for (size_t k = 0; k < comps_.size(); ++k) {
+        comps_[k]->join();  // copy-engine gather of the slot's runs (enqueues waits on the caller's stream)
+        if (!streams_.empty() && busy_[k]) ISB_CUDA(cudaStreamWaitEvent(caller, done_[k], 0));
+    }
+}
+
+void ComposerPool::sync()
+{
+    for (size_t k = 0; k < comps_.size(); ++k) {
+        if (!streams_.empty() && busy_[k]) {
+            ISB_CUDA(cudaEventSynchronize(done_[k]));
+            busy_[k] = 0;
+        }
+        comps_[k]->sync();
+    }
 }
 
 void Composer::byte_model(double* S, double* M, double* Ap, double* B)

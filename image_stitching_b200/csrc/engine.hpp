@@ -233,6 +233,7 @@ public:
     void plan(const isb_camera* cams, const int* sizes_wh, int n, int* corners, int* sizes, int* dst_roi);
     void run(const isb_image* imgs, const isb_gainmap* gains, const isb_mask* seams, int n, isb_pano* out);
     void sync();
+    void join();
     int timings(float* ms, int cap);
     void byte_model(double* S, double* M, double* Ap, double* B);
     static const char* stage_name(int i);
@@ -260,8 +261,47 @@ private:
     // descriptors of the last run as uploaded to imgs_dev_ (a run with identical descriptors skips the upload)
     std::vector<ImageDev> last_idev_;
     float last_ms_[8] = {};
+    // strip-sharded runs
+    std::vector<int> src_band_;   // per image [lo, hi]: source rows this strip can read (plan time, src_band_kernel)
+    DevBuf band_dev_;
+    size_t h2d_bytes_ = 0;        // source bytes the last run uploaded
+    // ISB_GATHER_COPY_ENGINE: local double-buffered strip + copy-engine push into the caller's (peer) panorama
+    DevBuf strip8_[2], stripm_[2];
+    cudaStream_t copy_stream_ = nullptr;
+    cudaEvent_t ev_done_[2] = {}, ev_copied_[2] = {};
+    unsigned long long run_count_ = 0;
+    bool copies_pending_ = false;
 public:
     ~Composer();
+    size_t last_h2d_bytes() const { return h2d_bytes_; }
+    const std::vector<int>& src_band() const { return src_band_; }
+};
+
+// isb_config::pipeline_depth > 1: that many Composers (own per-image pyramids, tables and stream each) served round-robin, so
+// that consecutive isb_composer_run() calls overlap on the device: the latency-bound coarse-level kernels of step k leave most
+// SMs idle, and the issue-bound kernels of step k + 1 fill them.  A run is then asynchronous with respect to the caller's
+// stream: its output is valid behind isb_composer_join() (stream-ordered) or after isb_composer_sync() (host), and runs in
+// flight must write to different output buffers.  Depth 1 is a plain Composer on the caller's stream.
+class ComposerPool {
+public:
+    explicit ComposerPool(const isb_config& cfg);
+    ~ComposerPool();
+    ComposerPool(const ComposerPool&) = delete;
+    ComposerPool& operator=(const ComposerPool&) = delete;
+    void plan(const isb_camera* cams, const int* sizes_wh, int n, int* corners, int* sizes, int* dst_roi);
+    void run(const isb_image* imgs, const isb_gainmap* gains, const isb_mask* seams, int n, isb_pano* out);
+    void sync();
+    void join();
+    Composer& first() { return *comps_[0]; }
+    Composer& last() { return *comps_[last_]; }
+    int depth() const { return (int)comps_.size(); }
+private:
+    std::vector<Composer*> comps_;
+    std::vector<cudaStream_t> streams_;
+    std::vector<cudaEvent_t> fork_, done_;
+    std::vector<char> busy_;
+    unsigned long long next_ = 0;
+    int last_ = 0;
 };
 
 }  // namespace isb

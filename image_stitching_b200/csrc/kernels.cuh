@@ -85,8 +85,9 @@ struct OccTile { int img; int left, top; int w, h; long long occ_off; };
 void launch_occupancy(const OccTile* tiles_dev, int n_tiles, int max_w, int max_h, const ImageDev* imgs, int nb,
                       uint8_t* occ, cudaStream_t st);
 // fused warp -> packed level 0
+// banded_sources: some ImageDev::band_lo is non-zero (see ImageDev)
 void launch_warp_tiles_packed(const WorkItem* work, int n_work, const TileDev* tiles, const ImageDev* imgs, int nb, uint32_t gen,
-                              cudaStream_t st);
+                              bool banded_sources, cudaStream_t st);
 // per-run seam preparation in one launch: (1) cv::dilate(3x3) of every image's seam mask, imgs[i].seam_raw -> imgs[i].seam;
 // (2) seam-aware culling: every macro cell that holds a valid pixel (plan-time occupancy) and in which the upsampled
 // dilated seam mask can be non-zero stamps `gen` into need[] for all cells within 4 cells of it.  One OccTile per image
@@ -105,6 +106,11 @@ constexpr int kTmaOutW = 64, kTmaOutH = 32;                          // outputs 
 constexpr int kTmaBoxW = 2 * kTmaOutW + 8, kTmaBoxH = 2 * kTmaOutH + 3;  // 136 x 67 input box (x origin 2*ox0 - 4)
 // 2x2-quad accumulate + normalise + collapse for level < nb
 void launch_blend_quad(const DstDev& dst, const TileDev* tiles, int level, const OutDev& out, cudaStream_t st);
+// rows [y0, y1) of `level` a run produces (level 0: the owned rows; coarser levels: what those rows reach through pyrUp)
+void blend_level_rows(const DstDev& dst, int level, int& y0, int& y1);
+// plan time: per-image [min, max] of the source rows the fused warp can read over the given blocks -> band[2 img], band[2 img + 1]
+// (initialise to INT_MAX / INT_MIN)
+void launch_src_band(const WorkItem* work, int n_work, const TileDev* tiles, const ImageDev* imgs, int* band, cudaStream_t st);
 
 constexpr int kFastDownCols = 64;   // output columns per warp (2 per lane)
 #ifndef ISB_DOWN_ROWS_L1

@@ -244,6 +244,7 @@ typedef struct isb_image { const uint8_t* data; int width, height; size_t pitch;
 typedef struct isb_gainmap { const float* data; int width, height; } isb_gainmap;                /* f32 grid; data NULL = no gain */
 typedef struct isb_mask { const uint8_t* data; int width, height; size_t pitch; } isb_mask;      /* 8UC1 seam mask; data NULL = all 255 */
 
+enum { ISB_GATHER_PEER_STORES = 0, ISB_GATHER_COPY_ENGINE = 1, ISB_GATHER_LOCAL = 2 };
 typedef struct isb_config {
     int warp_kind;            /* ISB_WARP_*  (warp_type, image_stitching.cpp:64) */
     float warped_image_scale; /* warper scale (image_stitching.cpp:1116-1117) */
@@ -254,7 +255,20 @@ typedef struct isb_config {
     int async_mode;           /* !=0: isb_composer_run() only enqueues (pinned host buffers must stay valid until
                                  isb_composer_sync()); lets two composers on two streams overlap one step's upload with
                                  the previous step's download */
-    int reserved[7];
+    int gather_mode;          /* strip-sharded runs with a device-resident isb_pano (ISB_GATHER_*):
+                                 PEER_STORES (0): the final kernel stores into isb_pano directly, as 16-byte vectors staged in
+                                   shared memory - over NVLink when isb_pano is rank 0's peer-mapped panorama;
+                                 COPY_ENGINE (1): the strip is composed into a local double-buffered block and pushed into
+                                   isb_pano (rank 0's panorama) by the copy engine on a second stream, overlapping the next
+                                   run's kernels; the rows have landed after isb_composer_sync() / behind isb_composer_join();
+                                 LOCAL (2): isb_pano is this GPU's own memory (rank 0): direct stores. */
+    int pipeline_depth;       /* > 1: that many runs may be in flight: consecutive isb_composer_run() calls are served by
+                                 independent pyramid sets on internal streams and overlap on the device (the latency-bound coarse
+                                 levels of one step under the issue-bound kernels of the next).  A run is then asynchronous with
+                                 respect to the caller's stream - its isb_pano is valid behind isb_composer_join() (stream-ordered)
+                                 or after isb_composer_sync() - and runs in flight must be given different output buffers.
+                                 0 / 1: one run at a time on the caller's stream. */
+    int reserved[5];
 } isb_config;
 
 /* Output of isb_compose: the panorama (dst_roi_final_ size).  data/mask describe the FULL panorama buffer
@@ -277,13 +291,20 @@ ISB_API int isb_composer_plan(isb_composer* c, const isb_camera* cams, const int
 /* Runs the loop on the planned geometry. gains / seam_masks may be NULL. */
 ISB_API int isb_composer_run(isb_composer* c, const isb_image* imgs, const isb_gainmap* gains, const isb_mask* seam_masks,
                              int n, isb_pano* out);
-/* waits for the last isb_composer_run() of this composer (needed only in async_mode) */
+/* waits for the last isb_composer_run() of this composer (needed only in async_mode / ISB_GATHER_COPY_ENGINE) */
 ISB_API int isb_composer_sync(isb_composer* c);
+/* stream-ordered variant for ISB_GATHER_COPY_ENGINE: work enqueued on the calling thread's stream after this call starts
+ * after the strips of all previous runs have landed in isb_pano (no host synchronisation) */
+ISB_API int isb_composer_join(isb_composer* c);
 /* device time (ms) of the last run split by stage; names via isb_composer_stage_name; returns #stages */
 ISB_API int isb_composer_last_timings(isb_composer* c, float* ms, int capacity);
 ISB_API const char* isb_composer_stage_name(int stage);
 /* algorithmic byte model of SURVEY.md 8(d) for the planned rig: S, M (valid warped px, counted on the device), A_p, B_alg */
 ISB_API int isb_composer_byte_model(isb_composer* c, double* S_px, double* M_px, double* Ap_px, double* B_alg_bytes);
+/* strip-sharded runs: rows [lo, hi] of source image `index` this strip reads (host sources are uploaded band-wise), and the
+ * source bytes the last isb_composer_run() copied host -> device */
+ISB_API int isb_composer_source_band(isb_composer* c, int index, int* row_lo, int* row_hi);
+ISB_API long long isb_composer_last_h2d_bytes(isb_composer* c);
 /* one-shot convenience == create + plan + run + destroy */
 ISB_API int isb_compose(const isb_image* imgs, const isb_camera* cams, const isb_gainmap* gains, const isb_mask* seam_masks,
                         int n, const isb_config* cfg, isb_pano* out);

@@ -71,6 +71,24 @@ def feather_sharpness(dst_w, dst_h, blend_strength=5.0):
     return float(np.float32(1.0) / (np.sqrt(np.float32(dst_w * dst_h)) * np.float32(blend_strength) / np.float32(100.0)))
 
 
+def warp_cv(warper, src, K, R, interp, border):
+    """warper.warp(src, K, R, interp, border).  cv::remap refuses destinations of SHRT_MAX columns or more
+    (imgwarp.cpp: `dst.cols < SHRT_MAX`), which a wrap-around image of a >= 32767-px-wide panorama (cfg3: 46654) hits - the
+    reference itself cannot stitch such a rig.  RotationWarperBase::warp is buildMaps + remap and remap is per-pixel, so for
+    those images the checker runs the same two calls with the maps cut into column chunks (identical arithmetic)."""
+    h, w = src.shape[:2]
+    x, y, rw, rh = warper.warpRoi((w, h), K, R)
+    if rw < 32767 and rh < 32767:
+        return warper.warp(src, K, R, interp, border)
+    roi, xmap, ymap = warper.buildMaps((w, h), K, R)
+    out = np.empty(xmap.shape + src.shape[2:], src.dtype)
+    for c0 in range(0, xmap.shape[1], 16384):
+        c1 = min(c0 + 16384, xmap.shape[1])
+        out[:, c0:c1] = cv2.remap(src, np.ascontiguousarray(xmap[:, c0:c1]), np.ascontiguousarray(ymap[:, c0:c1]), interp,
+                                  borderMode=border)
+    return (int(roi[0]), int(roi[1])), out
+
+
 def compose_cv(images, Ks, Rs, scale, kind, nb, gains=None, seam_masks=None, keep_stages=False,
                timings=None, blend_type="multiband", sharpness=None):
     """Mirror of the compositing loop.  Returns dict(corners, sizes, dst_roi, result16, result8, mask).
@@ -99,10 +117,10 @@ def compose_cv(images, Ks, Rs, scale, kind, nb, gains=None, seam_masks=None, kee
     tm = dict(warp_img=0.0, warp_mask=0.0, gain=0.0, to16s=0.0, seam=0.0, feed=0.0, blend=0.0)
     for i, (img, K, R) in enumerate(zip(images, Ks, Rs)):
         t0 = time.perf_counter()
-        corner, img_warped = warper.warp(img, K, R, cv2.INTER_LINEAR, cv2.BORDER_REFLECT)
+        corner, img_warped = warp_cv(warper, img, K, R, cv2.INTER_LINEAR, cv2.BORDER_REFLECT)
         t1 = time.perf_counter()
         mask = np.full(img.shape[:2], 255, np.uint8)
-        _, mask_warped = warper.warp(mask, K, R, cv2.INTER_NEAREST, cv2.BORDER_CONSTANT)
+        _, mask_warped = warp_cv(warper, mask, K, R, cv2.INTER_NEAREST, cv2.BORDER_CONSTANT)
         t2 = time.perf_counter()
         valid = mask_warped
         if comp is not None:
