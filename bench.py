@@ -357,6 +357,8 @@ def measure(name, div, args, rank, world, dev, stream, full):
         e1.record(stream)
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if os.environ.get("ISB_BENCH_DEBUG"):
+            sys.stderr.write(f"[debug] {name} rank {rank}: {float(ms.item()) / steps:.4f} ms/step over {steps} steps\n")
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
@@ -366,8 +368,9 @@ def measure(name, div, args, rank, world, dev, stream, full):
     steps = args.steps if full else max(5, min(args.steps, 20))
     isb.launch_count(reset=True)
     with ClockSampler(local) as clk:
-        ms_total = timed(step_device, steps, args.warmup, comp.join)
-    launches_per_step = isb.launch_count() // max(1, steps + args.warmup)
+        # warm-up touches every pyramid set and both staging blocks of every slot
+        ms_total = timed(step_device, steps, max(args.warmup, 2 * depth), comp.join)
+    launches_per_step = isb.launch_count() // max(1, steps + max(args.warmup, 2 * depth))
     ms_step = ms_total / steps
     res = {"rig": rig, "roi": roi, "ms_step": ms_step, "value": out_mp * steps / (ms_total / 1e3), "steps": steps, "plan_s": plan_s,
            "launches_per_step": int(launches_per_step), "clocks": clk.summary(), "gather": mode, "out_mp": out_mp,

@@ -68,7 +68,8 @@ class _Mask(C.Structure):
 class Config(C.Structure):
     _fields_ = [("warp_kind", C.c_int), ("warped_image_scale", C.c_float), ("num_bands", C.c_int),
                 ("strip_index", C.c_int), ("strip_count", C.c_int), ("cache_plan", C.c_int), ("async_mode", C.c_int),
-                ("gather_mode", C.c_int), ("pipeline_depth", C.c_int), ("reserved", C.c_int * 5)]
+                ("gather_mode", C.c_int), ("pipeline_depth", C.c_int), ("use_blend_rule", C.c_int),
+                ("blend_type", C.c_int), ("blend_strength", C.c_float), ("reserved", C.c_int * 2)]
 
 
 class _Pano(C.Structure):
@@ -670,6 +671,29 @@ def Timelapser_createDefault(ttype):
 # ---------------------------------------------------------------------------------------------------
 # fused loop
 # ---------------------------------------------------------------------------------------------------
+def crop_rect(mask, with_points=False):
+    """Rectangle (x, y, w, h) the reference's crop() (cropper.cpp:116-209) narrows the panorama to, from its 8UC1 mask
+    (numpy or torch.cuda, 2-D)."""
+    p, keep = _ptr(mask)
+    h, w = _shape(mask)[:2]
+    r = (C.c_int * 4)()
+    n = C.c_int(0)
+    _chk(lib().isb_crop_rect(C.c_void_p(p), int(w), int(h), C.c_size_t(int(w)), r, C.byref(n)))
+    return (tuple(r), n.value) if with_points else tuple(r)
+
+
+def crop(image):
+    """crop(source) of the reference: returns (cropped view, rect).  image: HxWx3 uint8 or int16 numpy array."""
+    a = np.ascontiguousarray(image)
+    assert a.ndim == 3 and a.shape[2] == 3 and a.dtype in (np.uint8, np.int16)
+    r = (C.c_int * 4)()
+    _chk(lib().isb_crop_rect_image(a.ctypes.data_as(C.c_void_p), a.shape[1], a.shape[0], C.c_size_t(a.strides[0]),
+                                   int(a.dtype == np.int16), r, None))
+    x, y, w, h = tuple(r)
+    out = np.clip(a, 0, 255).astype(np.uint8) if a.dtype == np.int16 else a  # crop() converts the source to CV_8U
+    return out[y:y + h, x:x + w], (x, y, w, h)
+
+
 def cameras_from_KR(Ks, Rs):
     """isb_camera list from float32 K = [[f,0,cx],[0,f*a,cy],[0,0,1]] and R."""
     cams = []
@@ -686,7 +710,7 @@ class Composer:
     """The whole compositing loop on the GPU (isb_composer_*)."""
 
     def __init__(self, warp="spherical", scale=1.0, num_bands=5, strip_index=0, strip_count=1, cache_plan=True,
-                 async_mode=False, gather_copy=False, gather_mode=None, pipeline_depth=1):
+                 async_mode=False, gather_copy=False, gather_mode=None, pipeline_depth=1, blend_type=None, blend_strength=5.0):
         self.cfg = Config()
         self.cfg.warp_kind = _KIND[warp]
         self.cfg.warped_image_scale = float(scale)
@@ -697,6 +721,10 @@ class Composer:
         # GATHER_PEER_STORES (0) / GATHER_COPY_ENGINE (1) / GATHER_LOCAL (2); gather_copy=True is shorthand for 1
         self.cfg.gather_mode = int(gather_mode) if gather_mode is not None else (GATHER_COPY_ENGINE if gather_copy else GATHER_PEER_STORES)
         self.cfg.pipeline_depth = int(pipeline_depth)
+        if blend_type is not None:  # the reference's blender set-up (image_stitching.cpp:1173-1193) instead of explicit num_bands
+            self.cfg.use_blend_rule = 1
+            self.cfg.blend_type = {"no": BLENDER_NO, "feather": BLENDER_FEATHER, "multiband": BLENDER_MULTI_BAND}.get(blend_type, blend_type)
+            self.cfg.blend_strength = float(blend_strength)
         self._h = C.c_void_p(lib().isb_composer_create(C.byref(self.cfg)))
         self.n = 0
 

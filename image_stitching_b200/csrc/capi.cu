@@ -422,6 +422,16 @@ int isb_timelapser_get_dst(isb_timelapser* t, int16_t* dst, size_t dpitch)
     return guarded([&] { NOT_NULL(t); t->impl.get_dst(dst, dpitch); });
 }
 
+// ---- crop -------------------------------------------------------------------------------------------
+int isb_crop_rect(const uint8_t* mask, int w, int h, size_t pitch, int rect[4], int* n_points)
+{
+    return guarded([&] { crop_rect(mask, w, h, pitch, rect, n_points); });
+}
+int isb_crop_rect_image(const void* img, int w, int h, size_t pitch, int is_16s, int rect[4], int* n_points)
+{
+    return guarded([&] { crop_rect_image(img, w, h, pitch, is_16s, rect, n_points); });
+}
+
 // ---- composer ---------------------------------------------------------------------------------------
 isb_composer* isb_composer_create(const isb_config* cfg)
 {

@@ -773,8 +773,32 @@ void Composer::plan(const isb_camera* cams, const int* sizes_wh, int n, int* cor
             ss[2 * i] = img_[i].roi.w; ss[2 * i + 1] = img_[i].roi.h;
         }
         dst_roi_ = result_roi(cs.data(), ss.data(), n);
+        // which blender (image_stitching.cpp:1173-1193)
+        eff_blend_type_ = ISB_BLENDER_MULTI_BAND;
+        eff_num_bands_ = cfg_.num_bands;
+        if (cfg_.use_blend_rule) {
+            ISB_ASSERT(cfg_.blend_type == ISB_BLENDER_NO || cfg_.blend_type == ISB_BLENDER_FEATHER || cfg_.blend_type == ISB_BLENDER_MULTI_BAND);
+            const float blend_width = std::sqrt(static_cast<float>((long long)dst_roi_.w * dst_roi_.h)) * cfg_.blend_strength / 100.f;
+            eff_blend_type_ = cfg_.blend_type;
+            if (blend_width < 1.f) eff_blend_type_ = ISB_BLENDER_NO;
+            else if (eff_blend_type_ == ISB_BLENDER_MULTI_BAND)
+                eff_num_bands_ = static_cast<int>(std::ceil(std::log(blend_width) / std::log(2.)) - 1.);
+            else if (eff_blend_type_ == ISB_BLENDER_FEATHER) eff_sharpness_ = 1.f / blend_width;
+        }
+        ISB_ASSERT(eff_num_bands_ >= 0);
+        if (eff_blend_type_ != ISB_BLENDER_MULTI_BAND) {
+            // Blender::NO / FeatherBlender: no pyramids to plan; run() drives the per-call kernels over the planned ROIs
+            ISB_ASSERT(cfg_.strip_count == 1);
+            planned_ = true;
+            for (int i = 0; i < n; ++i) {
+                if (corners) { corners[2 * i] = img_[i].roi.x; corners[2 * i + 1] = img_[i].roi.y; }
+                if (sizes) { sizes[2 * i] = img_[i].roi.w; sizes[2 * i + 1] = img_[i].roi.h; }
+            }
+            if (dst_roi) { dst_roi[0] = dst_roi_.x; dst_roi[1] = dst_roi_.y; dst_roi[2] = dst_roi_.w; dst_roi[3] = dst_roi_.h; }
+            return;
+        }
         BlendGeometry g;
-        g.prepare(dst_roi_, cfg_.num_bands);
+        g.prepare(dst_roi_, eff_num_bands_);
         // strip: owned rows on the 2^nb grid + halo rows computed redundantly.  With m = 2^nb and strip cuts on the m grid,
         // output rows [y0, y1) read collapsed rows [y0 / 2^l - 2, y1 / 2^l + 1] of level l (fine rows [a, b] read coarse rows
         // [a/2 - 1, b/2 + 1]); a level-l row q of an image pyramid reads level-0 rows [2^l q - 2 (2^l - 1), 2^l q + 2 (2^l - 1)],
@@ -929,6 +953,10 @@ void Composer::run(const isb_image* imgs, const isb_gainmap* gains, const isb_ma
     if (!planned_) throw Error(ISB_ERR_ASSERT, "Assertion failed: isb_composer_plan() must precede isb_composer_run()");
     if (!imgs || !out) throw Error(ISB_ERR_NULL_PTR, "imgs/out are null");
     ISB_ASSERT(n == (int)img_.size());
+    if (eff_blend_type_ != ISB_BLENDER_MULTI_BAND) {
+        run_simple(imgs, gains, seams, n, out);
+        return;
+    }
     cudaStream_t st = current_stream();
     if (!ev_init_) {
         for (auto& e : ev_) ISB_CUDA(cudaEventCreate(&e));
@@ -1140,8 +1168,12 @@ void Composer::run(const isb_image* imgs, const isb_gainmap* gains, const isb_ma
         slot = (int)(run_count_ & 1);
         if (run_count_ >= 2) ISB_CUDA(cudaStreamWaitEvent(st, ev_copied_[slot], 0));  // the slot's previous strip has left
         const size_t rows = (size_t)(oy1 - oy0);
-        uint8_t* s8 = static_cast<uint8_t*>(strip8_[slot].ensure(out->pitch * rows));
-        uint8_t* sm = static_cast<uint8_t*>(stripm_[slot].ensure(out->mask_pitch * rows));
+        for (int k = 0; k < 2; ++k) {  // both staging blocks at once: an allocation stalls everything in flight on the device
+            strip8_[k].ensure(out->pitch * rows);
+            stripm_[k].ensure(out->mask_pitch * rows);
+        }
+        uint8_t* s8 = strip8_[slot].as<uint8_t>();
+        uint8_t* sm = stripm_[slot].as<uint8_t>();
         o.out8 = s8 - (long long)(oy0 - sub0) * o.pitch8;
         o.mask = sm - (long long)(oy0 - sub0) * o.mpitch;
         o.peer = 0;
@@ -1174,6 +1206,76 @@ void Composer::run(const isb_image* imgs, const isb_gainmap* gains, const isb_ma
     for (int i = 0; i < n && !any_host; ++i)
         if (!tiles_of_image_[i].empty() && mem_kind(imgs[i].data) == MemKind::Host) any_host = true;
     if (any_host && !cfg_.async_mode) ISB_CUDA(cudaStreamSynchronize(st));
+}
+
+// Blender::NO / FeatherBlender (image_stitching.cpp:1086-1229 with blend_type no / feather): the loop call by call, every
+// intermediate on the device - warp of the image and of the all-255 mask, compensator apply, convertTo(16S), seam mask
+// dilate + INTER_LINEAR_EXACT + AND, feed, blend, saturate to 8U.
+void Composer::run_simple(const isb_image* imgs, const isb_gainmap* gains, const isb_mask* seams, int n, isb_pano* out)
+{
+    cudaStream_t st = current_stream();
+    SimpleBlender blender(eff_blend_type_, eff_sharpness_);
+    blender.prepare(dst_roi_);
+    Warper warper(cfg_.warp_kind, cfg_.warped_image_scale);
+    DevBuf warped, ones, maskw, img16;
+    for (int i = 0; i < n; ++i) {
+        const isb_image& im = imgs[i];
+        if (!im.data) throw Error(ISB_ERR_NULL_PTR, "image data is null");
+        ISB_ASSERT(im.width == img_[i].src_w && im.height == img_[i].src_h && im.pitch >= (size_t)im.width * 3);
+        const Rect roi = img_[i].roi;
+        float K[9];
+        isb_camera_K(&cams_[i], K);
+        uint8_t* w8 = static_cast<uint8_t*>(warped.ensure((size_t)roi.w * 3 * roi.h));
+        uint8_t* m1 = static_cast<uint8_t*>(ones.ensure((size_t)im.width * im.height));
+        uint8_t* mw = static_cast<uint8_t*>(maskw.ensure((size_t)roi.w * roi.h));
+        int16_t* i16 = static_cast<int16_t*>(img16.ensure((size_t)roi.w * 6 * roi.h));
+        ISB_CUDA(cudaMemsetAsync(m1, 255, (size_t)im.width * im.height, st));
+        warper.warp(im.data, im.width, im.height, 3, im.pitch, K, cams_[i].R, ISB_INTER_LINEAR, ISB_BORDER_REFLECT, w8, (size_t)roi.w * 3, nullptr);
+        warper.warp(m1, im.width, im.height, 1, (size_t)im.width, K, cams_[i].R, ISB_INTER_NEAREST, ISB_BORDER_CONSTANT, mw, (size_t)roi.w, nullptr);
+        if (gains && gains[i].data) {
+            const isb_gainmap& g = gains[i];
+            ISB_ASSERT(g.width > 0 && g.height > 0);
+            std::vector<float> gh((size_t)g.width * g.height);
+            ISB_CUDA(cudaMemcpyAsync(gh.data(), g.data, gh.size() * sizeof(float), cudaMemcpyDefault, st));
+            ISB_CUDA(cudaStreamSynchronize(st));
+            Compensator comp(64, 64);
+            const float* gp = gh.data();
+            comp.set_gains(1, &gp, &g.width, &g.height);
+            comp.apply(0, w8, roi.w, roi.h, (size_t)roi.w * 3);
+        }
+        if (seams && seams[i].data) {
+            const isb_mask& m = seams[i];
+            ISB_ASSERT(m.width > 0 && m.height > 0 && m.pitch >= (size_t)m.width);
+            seam_mask_apply(m.data, m.width, m.height, m.pitch, mw, roi.w, roi.h, (size_t)roi.w);
+        }
+        launch_convert_8u16s(w8, (long long)roi.w * 3, i16, (long long)roi.w * 6, roi.w * 3, roi.h, st);
+        blender.feed(i16, (size_t)roi.w * 6, mw, (size_t)roi.w, roi.w, roi.h, roi.x, roi.y);
+    }
+    const int W = dst_roi_.w, H = dst_roi_.h;
+    int16_t* r16 = static_cast<int16_t*>(out16_.ensure((size_t)W * 6 * H));
+    const bool dm = out->mask && mem_kind(out->mask) == MemKind::Device;
+    uint8_t* rm = dm ? out->mask : static_cast<uint8_t*>(outm_.ensure((size_t)W * H));
+    const size_t rmp = dm ? out->mask_pitch : (size_t)W;
+    if (out->mask) ISB_ASSERT(out->mask_pitch >= (size_t)W);
+    blender.blend(r16, (size_t)W * 6, rm, rmp);
+    if (out->mask && !dm) copy2d(out->mask, out->mask_pitch, rm, rmp, W, H, st);
+    if (out->data) {
+        ISB_ASSERT(out->pitch >= (size_t)W * 3);
+        const bool d8 = mem_kind(out->data) == MemKind::Device;
+        uint8_t* r8 = d8 ? out->data : static_cast<uint8_t*>(out8_.ensure((size_t)W * 3 * H));
+        const size_t p8 = d8 ? out->pitch : (size_t)W * 3;
+        launch_convert_16s8u(r16, (long long)W * 6, r8, (long long)p8, W * 3, H, st);
+        if (!d8) copy2d(out->data, out->pitch, r8, p8, (size_t)W * 3, H, st);
+    }
+    if (out->data16) {
+        ISB_ASSERT(out->pitch16 >= (size_t)W * 6);
+        copy2d(out->data16, out->pitch16, r16, (size_t)W * 6, (size_t)W * 6, H, st);
+    }
+    ISB_CUDA(cudaGetLastError());
+    ISB_CUDA(cudaStreamSynchronize(st));
+    out->roi_xywh[0] = dst_roi_.x; out->roi_xywh[1] = dst_roi_.y; out->roi_xywh[2] = W; out->roi_xywh[3] = H;
+    out->strip_y0 = 0;
+    out->strip_y1 = H;
 }
 
 void Composer::join()

@@ -169,6 +169,10 @@ void rotate_image(const uint8_t* src, int w, int h, int ch, size_t spitch, int c
 void resize_linear_exact(const uint8_t* src, int sw, int sh, int ch, size_t spitch, uint8_t* dst, int dw, int dh, size_t dpitch,
                          double fx, double fy);
 
+// crop() of the reference (cropper.cpp:116-209) on the device: crop.cu
+void crop_rect(const uint8_t* mask, int W, int H, size_t pitch, int rect_xywh[4], int* n_points);
+void crop_rect_image(const void* img, int W, int H, size_t pitch, int is_16s, int rect_xywh[4], int* n_points);
+
 void seam_mask_apply(const uint8_t* seam, int mw, int mh, size_t spitch, uint8_t* mask, int w, int h, size_t pitch);
 
 class Blender {
@@ -237,7 +241,14 @@ public:
     int timings(float* ms, int cap);
     void byte_model(double* S, double* M, double* Ap, double* B);
     static const char* stage_name(int i);
+    // the blender the reference's rule selects for the planned panorama (image_stitching.cpp:1173-1193)
+    int effective_blend_type() const { return eff_blend_type_; }
+    int effective_num_bands() const { return eff_num_bands_; }
+    float effective_sharpness() const { return eff_sharpness_; }
 private:
+    void run_simple(const isb_image* imgs, const isb_gainmap* gains, const isb_mask* seams, int n, isb_pano* out);
+    int eff_blend_type_ = ISB_BLENDER_MULTI_BAND, eff_num_bands_ = 0;
+    float eff_sharpness_ = 0.02f;
     bool same_plan(const isb_camera* cams, const int* sizes_wh, int n) const;
     isb_config cfg_;
     bool planned_ = false;

@@ -213,13 +213,26 @@ void BlendGeometry::tile_rect(int w, int h, int tlx, int tly, int tl_new[2], int
     br_new[0] = bx - dx; br_new[1] = by - dy;
 }
 
+// Strip cuts on the 2^nb grid, balanced by WORK rather than by rows: a strip recomputes a halo of 4 cell rows above and 3
+// below (Composer::plan), except at the panorama's own top / bottom.  With c cell rows per interior strip the first strip
+// gets c + 4 and the last c + 3 (each saves one halo), so every strip warps about c + 7 cell rows; the remainder goes to
+// the leading strips.  Pure arithmetic: every rank computes every rank's rows.
 void strip_rows(int padded_h, int nb, int strip_index, int strip_count, int& y0, int& y1)
 {
     const int cells = padded_h >> nb;  // padded_h is a multiple of 2^nb
-    const int c0 = (int)((long long)cells * strip_index / strip_count);
-    const int c1 = (int)((long long)cells * (strip_index + 1) / strip_count);
-    y0 = c0 << nb;
-    y1 = c1 << nb;
+    const int n = strip_count;
+    auto cut = [&](int i) -> int {     // first cell row of strip i (i in [0, n])
+        if (i <= 0) return 0;
+        if (i >= n) return cells;
+        if (n == 1) return cells;
+        const int c = (cells - 7) / n;  // interior strips
+        if (c < 1) return (int)((long long)cells * i / n);  // panorama too short for the scheme: plain equal cuts
+        const int rem = (cells - 7) - c * n;
+        // strips 0 .. i-1: the first one is 4 taller; `rem` extra rows go one each to the leading strips
+        return 4 + c * i + (i < rem ? i : rem);
+    };
+    y0 = cut(strip_index) << nb;
+    y1 = cut(strip_index + 1) << nb;
 }
 
 }  // namespace isb

@@ -415,6 +415,34 @@ __global__ void __launch_bounds__(256) blend_level_kernel(DstDev D, const TileDe
     }
 }
 
+// ---- depth conversions of the loop: convertTo(CV_16S) (image_stitching.cpp:1164) and the saturate to 8U of imwrite (:1228) ----
+__global__ void __launch_bounds__(256) convert_8u16s_kernel(const uint8_t* __restrict__ src, long long spitch, int16_t* __restrict__ dst,
+                                                            long long dpitch_bytes, int row_elems, int h)
+{
+    const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y;
+    if (x >= row_elems || y >= h) return;
+    reinterpret_cast<int16_t*>(reinterpret_cast<char*>(dst) + (long long)y * dpitch_bytes)[x] = src[(long long)y * spitch + x];
+}
+__global__ void __launch_bounds__(256) convert_16s8u_kernel(const int16_t* __restrict__ src, long long spitch_bytes, uint8_t* __restrict__ dst,
+                                                            long long dpitch, int row_elems, int h)
+{
+    const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y;
+    if (x >= row_elems || y >= h) return;
+    dst[(long long)y * dpitch + x] = (uint8_t)sat_u8(reinterpret_cast<const int16_t*>(reinterpret_cast<const char*>(src) + (long long)y * spitch_bytes)[x]);
+}
+void launch_convert_8u16s(const uint8_t* src, long long spitch, int16_t* dst, long long dpitch_bytes, int row_elems, int h, cudaStream_t st)
+{
+    if (row_elems <= 0 || h <= 0) return;
+    convert_8u16s_kernel<<<dim3((row_elems + 255) / 256, h), 256, 0, st>>>(src, spitch, dst, dpitch_bytes, row_elems, h);
+    ISB_COUNT_LAUNCH();
+}
+void launch_convert_16s8u(const int16_t* src, long long spitch_bytes, uint8_t* dst, long long dpitch, int row_elems, int h, cudaStream_t st)
+{
+    if (row_elems <= 0 || h <= 0) return;
+    convert_16s8u_kernel<<<dim3((row_elems + 255) / 256, h), 256, 0, st>>>(src, spitch_bytes, dst, dpitch, row_elems, h);
+    ISB_COUNT_LAUNCH();
+}
+
 void launch_blend_level(const DstDev& dst, const TileDev* tiles, int level, const OutDev& out, cudaStream_t st)
 {
     const int pw = dst.pw >> level;

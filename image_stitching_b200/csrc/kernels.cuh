@@ -62,6 +62,10 @@ void launch_seam_and(const uint8_t* dil, int mw, int mh, const uint32_t* mx, con
 void launch_pack_tile(const TileDev* tile_dev, const TileDev& tile_host, const int16_t* img, long long ipitch,
                       const uint8_t* mask, long long mpitch, cudaStream_t st);
 
+// element-wise depth conversions (row_elems = width * channels): convertTo(CV_16S) and saturate_cast<uchar>
+void launch_convert_8u16s(const uint8_t* src, long long spitch, int16_t* dst, long long dpitch_bytes, int row_elems, int h, cudaStream_t st);
+void launch_convert_16s8u(const int16_t* src, long long spitch_bytes, uint8_t* dst, long long dpitch, int row_elems, int h, cudaStream_t st);
+
 // ingest pre-steps of the compositing loop (image_stitching.cpp:1093-1103, 1143-1146)
 // cv::rotate: code 0 = ROTATE_90_CLOCKWISE (dst is h x w), 1 = ROTATE_180
 void launch_rotate(const uint8_t* src, int w, int h, int ch, long long spitch, int code, uint8_t* dst, long long dpitch,

@@ -268,7 +268,15 @@ typedef struct isb_config {
                                  respect to the caller's stream - its isb_pano is valid behind isb_composer_join() (stream-ordered)
                                  or after isb_composer_sync() - and runs in flight must be given different output buffers.
                                  0 / 1: one run at a time on the caller's stream. */
-    int reserved[5];
+    int use_blend_rule;       /* 0: MultiBandBlender with `num_bands` as given (setNumBands).  !=0: the reference's own blender
+                                 set-up (image_stitching.cpp:1173-1193) from `blend_type` and `blend_strength`:
+                                 blend_width = sqrt(dst_area) * blend_strength / 100; blend_width < 1 -> Blender::NO;
+                                 MULTI_BAND -> num_bands = ceil(log(blend_width) / log(2)) - 1; FEATHER -> sharpness = 1 / blend_width.
+                                 NO / FEATHER run the loop (warp, mask warp, gain, ->16S, seam mask, feed, blend) on the device
+                                 with the per-call kernels; strips and pipeline_depth apply to MULTI_BAND only. */
+    int blend_type;           /* ISB_BLENDER_NO / ISB_BLENDER_FEATHER / ISB_BLENDER_MULTI_BAND (blend_type, image_stitching.cpp:80) */
+    float blend_strength;     /* blend_strength, image_stitching.cpp:81 (default 5) */
+    int reserved[2];
 } isb_config;
 
 /* Output of isb_compose: the panorama (dst_roi_final_ size).  data/mask describe the FULL panorama buffer
@@ -308,6 +316,21 @@ ISB_API long long isb_composer_last_h2d_bytes(isb_composer* c);
 /* one-shot convenience == create + plan + run + destroy */
 ISB_API int isb_compose(const isb_image* imgs, const isb_camera* cams, const isb_gainmap* gains, const isb_mask* seam_masks,
                         int n, const isb_config* cfg, isb_pano* out);
+
+/* ============================================================================================
+ * crop() of the reference (image_stitching/cropper.cpp:116-209): the largest-interior-rectangle
+ * heuristic - biggest external contour, its filled mask, a rectangle shrunk side by side until its border holds no exterior
+ * pixel (checkInteriorExterior, cropper.cpp:6-104).  The reference derives its mask from the image (`gray > 0`, :118-124);
+ * the north star runs it on the composited mask, so both forms are offered.  Returns the rectangle {x, y, width, height}
+ * crop() would narrow the image to (source = source(croppingMask)); the caller crops by pointer arithmetic.
+ * ISB_ERR_OUT_OF_RANGE when the mask is empty (the reference's contours.at(0) throws).
+ * ============================================================================================ */
+/* mask: 8UC1, non-zero = inside (isb_pano.mask); host or device pointer.  n_contour_points (may be NULL): size of the
+ * chosen contour as cv::findContours(RETR_EXTERNAL, CHAIN_APPROX_NONE) reports it. */
+ISB_API int isb_crop_rect(const uint8_t* mask, int width, int height, size_t pitch, int rect_xywh[4], int* n_contour_points);
+/* the literal crop(source): image 8UC3 (is_16s = 0) or 16SC3 (is_16s = 1, what blend() returns; saturated to 8U first) */
+ISB_API int isb_crop_rect_image(const void* image, int width, int height, size_t pitch_bytes, int is_16s, int rect_xywh[4],
+                                int* n_contour_points);
 
 /* Peer-memory plumbing for the fused "collapse + gather" of the strip-sharded path: rank 0 allocates the panorama
  * with isb_device_malloc and exports it; the other ranks open the handle and pass the returned pointer as

@@ -17,6 +17,7 @@ REF_DIR = "/root/reference/image_stitching"
 EULER = {"XYZ": 0, "YXZ": 1, "ZXY": 2, "ZYX": 3, "YZX": 4, "XZY": 5}
 _LIB = None
 _KEEP = []  # ctypes callbacks must outlive their registration
+_BUFS = []  # arrays handed to the C side by the last few findContours calls
 
 
 def build(force: bool = False):
@@ -184,8 +185,8 @@ def install_cv2_contours():
         contours, _ = cv2.findContours(m, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_NONE)
         xy = np.ascontiguousarray(np.concatenate([c.reshape(-1, 2) for c in contours]) if contours else np.zeros((0, 2)), np.int32)
         lens = np.ascontiguousarray([len(c) for c in contours], np.int32)
-        _KEEP.append((xy, lens))
-        del _KEEP[:-4]
+        _BUFS.append((xy, lens))
+        del _BUFS[:-4]
         xy_out[0] = xy.ctypes.data_as(C.POINTER(C.c_int))
         lens_out[0] = lens.ctypes.data_as(C.POINTER(C.c_int))
         n_out[0] = len(contours)

@@ -465,6 +465,37 @@ def test_loop_with_simple_blenders(tag):
     assert np.abs(out["result8"].astype(int) - cv8.astype(int)).max() <= MAX_ABS and psnr(out["result8"], cv8) >= MIN_PSNR
 
 
+@pytest.mark.parametrize("tag", ["feather", "no", "multiband"])
+def test_fused_composer_serves_all_three_blenders(tag):
+    """isb_config.use_blend_rule: the C composer applies the reference's own blender set-up (image_stitching.cpp:1173-1193:
+    blend_width from the panorama area and blend_strength -> Blender::NO / FeatherBlender sharpness / band count) and runs the
+    whole loop on the device for every blender type - bit-exact against the loop composed from the oracle."""
+    from test_oracle_golden import oracle_loop_with_blender
+    rig, imgs, gains, nb = make_case("cfg2", 16, 3)
+    seams = seam_masks_oracle(rig)
+    c = isb.Composer(rig.warp, rig.scale, 99, blend_type=tag, blend_strength=5.0)  # num_bands is ignored under the rule
+    _, _, roi = c.plan(isb.cameras_from_KR(rig.Ks, rig.Rs), [(rig.W, rig.H)] * rig.n)
+    out = c.run(imgs, gains, seams, want16=True)
+    bw = float(np.sqrt(np.float32(roi[2] * roi[3])) * np.float32(5.0) / np.float32(100.0))
+    assert bw >= 1
+    if tag == "multiband":
+        bands = int(np.ceil(np.log(bw) / np.log(2.0)) - 1.0)
+        assert bands == isb.num_bands_for(roi[2], roi[3], 5.0)
+        ref = orc.compose(imgs, rig.Ks, rig.Rs, rig.scale, rig.warp, bands, gains, seams)
+    else:
+        sharp = float(np.float32(1.0) / np.float32(bw))
+        ref = oracle_loop_with_blender(rig, imgs, gains, seams, orc.SimpleBlender(1 if tag == "feather" else 0, sharp))
+    assert tuple(out["dst_roi"]) == tuple(ref["dst_roi"])
+    assert np.array_equal(out["mask"], ref["mask"]) and np.array_equal(out["result16"], ref["result16"])
+    assert np.array_equal(out["result8"], np.clip(ref["result16"], 0, 255).astype(np.uint8))
+    # a tiny blend_strength makes blend_width < 1: every type falls back to Blender::NO (image_stitching.cpp:1178-1179)
+    c0 = isb.Composer(rig.warp, rig.scale, 3, blend_type=tag, blend_strength=1e-4)
+    c0.plan(isb.cameras_from_KR(rig.Ks, rig.Rs), [(rig.W, rig.H)] * rig.n)
+    out0 = c0.run(imgs, gains, seams, want16=True)
+    ref0 = oracle_loop_with_blender(rig, imgs, gains, seams, orc.SimpleBlender(0, 0.02))
+    assert np.array_equal(out0["mask"], ref0["mask"]) and np.array_equal(out0["result16"], ref0["result16"])
+
+
 def test_seam_aware_culling_follows_the_masks_of_each_run():
     """The per-run need map must track the seam masks actually passed: same cached plan, different masks (incl. all-zero for
     one image, none at all, and masks that keep only a corner), every run bit-exact against the oracle."""
