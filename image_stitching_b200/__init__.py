@@ -397,6 +397,21 @@ class RotationWarper:
         return (c[0], c[1]), dst
 
 
+    def warpBackward(self, src, K, R, interp_mode, border_mode, dst_size):
+        """cv2.PyRotationWarper.warpBackward: src = warped image of warpRoi(dst_size) pixels; returns the dst_size = (w, h) frame."""
+        src = np.ascontiguousarray(src, np.uint8)
+        h, w = src.shape[:2]
+        ch = 1 if src.ndim == 2 else src.shape[2]
+        dw, dh = int(dst_size[0]), int(dst_size[1])
+        dst = np.empty((dh, dw) if src.ndim == 2 else (dh, dw, ch), np.uint8)
+        Kp, _k = _f32p(K)
+        Rp, _r = _f32p(R)
+        _chk(lib().isb_warper_warp_backward(self._h, src.ctypes.data_as(C.c_void_p), w, h, ch, C.c_size_t(w * ch), Kp, Rp,
+                                            int(interp_mode), int(border_mode), dw, dh, dst.ctypes.data_as(C.c_void_p),
+                                            C.c_size_t(dw * ch)))
+        return dst
+
+
 # ---------------------------------------------------------------------------------------------------
 # cv::detail::BlocksGainCompensator (apply side)
 # ---------------------------------------------------------------------------------------------------

@@ -250,6 +250,11 @@ int isb_warper_warp(isb_warper* w, const uint8_t* src, int sw, int sh, int ch, s
 {
     return guarded([&] { NOT_NULL(w); w->impl.warp(src, sw, sh, ch, spitch, K, R, interp, border, dst, dpitch, corner); });
 }
+int isb_warper_warp_backward(isb_warper* w, const uint8_t* src, int sw, int sh, int ch, size_t spitch, const float* K, const float* R,
+                             int interp, int border, int dw, int dh, uint8_t* dst, size_t dpitch)
+{
+    return guarded([&] { NOT_NULL(w); w->impl.warp_backward(src, sw, sh, ch, spitch, K, R, interp, border, dw, dh, dst, dpitch); });
+}
 
 // ---- compensator / seam -----------------------------------------------------------------------------
 isb_compensator* isb_compensator_create(int bw, int bh) { return new (std::nothrow) isb_compensator(bw, bh); }

@@ -477,6 +477,48 @@ void Warper::warp(const uint8_t* src, int sw, int sh, int ch, size_t spitch, con
     }
 }
 
+void Warper::warp_backward(const uint8_t* src, int sw, int sh, int ch, size_t spitch, const float* K, const float* R, int interp,
+                           int border, int dw, int dh, uint8_t* dst, size_t dpitch)
+{
+    require_device();
+    check_KR(K, R);
+    if (!src || !dst) throw Error(ISB_ERR_NULL_PTR, "src/dst are null");
+    ISB_ASSERT(ch == 1 || ch == 3);
+    ISB_ASSERT(interp == ISB_INTER_NEAREST || interp == ISB_INTER_LINEAR);
+    ISB_ASSERT(border == ISB_BORDER_CONSTANT || border == ISB_BORDER_REFLECT);
+    ISB_ASSERT(dw > 0 && dh > 0 && sw > 0 && sh > 0 && spitch >= (size_t)sw * ch && dpitch >= (size_t)dw * ch);
+    Projector p;
+    p.set(kind_, scale_, K, R);
+    const Rect roi = p.warp_roi(dw, dh);
+    // CV_Assert(src_br.x - src_tl.x + 1 == size.width && src_br.y - src_tl.y + 1 == size.height)
+    ISB_ASSERT(roi.w == sw && roi.h == sh);
+    cudaStream_t st = current_stream();
+    ImageDev I{};
+    I.sw = sw;
+    I.sh = sh;
+    if (mem_kind(src) == MemKind::Device) {
+        I.src = src;
+        I.spitch = (long long)spitch;
+    } else {
+        const size_t sp = (size_t)sw * ch;
+        uint8_t* d = static_cast<uint8_t*>(src_.ensure(sp * sh));
+        copy2d(d, sp, src, spitch, sp, sh, st);
+        I.src = d;
+        I.spitch = (long long)sp;
+    }
+    const bool ddev = mem_kind(dst) == MemKind::Device;
+    uint8_t* dd = dst;
+    size_t dp = dpitch;
+    if (!ddev) {
+        dp = (size_t)dw * ch;
+        dd = static_cast<uint8_t*>(dst_.ensure(dp * dh));
+    }
+    launch_warp_backward(I, ch, p.r_kinv, scale_, kind_ == ISB_WARP_SPHERICAL ? 1 : 0, roi.x, roi.y, interp, border, dw, dh, dd, (long long)dp, st);
+    if (!ddev) copy2d(dst, dpitch, dd, dp, (size_t)dw * ch, dh, st);
+    ISB_CUDA(cudaGetLastError());
+    ISB_CUDA(cudaStreamSynchronize(st));
+}
+
 // ------------------------------------------------------------------------------------------------
 // Compensator / seam mask
 // ------------------------------------------------------------------------------------------------

@@ -143,6 +143,9 @@ public:
     Rect build_maps(int sw, int sh, const float* K, const float* R, float* xmap, float* ymap, size_t pitch);
     void warp(const uint8_t* src, int sw, int sh, int ch, size_t spitch, const float* K, const float* R, int interp,
               int border, uint8_t* dst, size_t dpitch, int* corner);
+    // warpBackward(src = warped image of size warpRoi(dst_size), ..., dst_size, dst)
+    void warp_backward(const uint8_t* src, int sw, int sh, int ch, size_t spitch, const float* K, const float* R, int interp,
+                       int border, int dw, int dh, uint8_t* dst, size_t dpitch);
 private:
     void prepare_image(int sw, int sh, const float* K, const float* R, ImageDev& I, Rect& roi, cudaStream_t st);
     int kind_;

@@ -14,6 +14,7 @@
 
 #include "kernels.cuh"
 #include "device_math.cuh"
+#include "glibc_math.cuh"
 
 namespace isb {
 
@@ -72,6 +73,69 @@ __global__ void __launch_bounds__(256) warp_generic_kernel(ImageDev I, int inter
     }
 #pragma unroll
     for (int c = 0; c < CH; ++c) dst[(long long)y * dpitch + x * CH + c] = (uint8_t)v[c];
+}
+
+// RotationWarperBase::warpBackward: for every pixel (x, y) of the ORIGINAL image the forward map (u, v) - transcendentals per
+// pixel, evaluated with glibc's float algorithms (glibc_math.cuh) - then cv::remap of the warped image at (u - tl.x, v - tl.y)
+struct BackwardDev {
+    float r_kinv[9];
+    float scale;
+    int spherical;
+    int tlx, tly;
+};
+template <int CH>
+__global__ void __launch_bounds__(256) warp_backward_kernel(ImageDev I, BackwardDev B, int interp, int border, int dw, int dh,
+                                                            uint8_t* __restrict__ dst, long long dpitch)
+{
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= dw || y >= dh) return;
+    const float fx = (float)x, fy = (float)y;
+    const float* r = B.r_kinv;
+    const float x_ = __fadd_rn(__fadd_rn(__fmul_rn(r[0], fx), __fmul_rn(r[1], fy)), r[2]);
+    const float y_ = __fadd_rn(__fadd_rn(__fmul_rn(r[3], fx), __fmul_rn(r[4], fy)), r[5]);
+    const float z_ = __fadd_rn(__fadd_rn(__fmul_rn(r[6], fx), __fmul_rn(r[7], fy)), r[8]);
+    const float u = __fmul_rn(B.scale, gm::atan2f_(x_, z_));
+    float v;
+    if (B.spherical) {
+        const float n2 = __fadd_rn(__fadd_rn(__fmul_rn(x_, x_), __fmul_rn(y_, y_)), __fmul_rn(z_, z_));
+        const float w = __fdiv_rn(y_, __fsqrt_rn(n2));
+        v = __fmul_rn(B.scale, __fsub_rn(3.14159274101257324f, gm::acosf_(w == w ? w : 0.f)));
+    } else {
+        v = __fdiv_rn(__fmul_rn(B.scale, y_), __fsqrt_rn(__fadd_rn(__fmul_rn(x_, x_), __fmul_rn(z_, z_))));
+    }
+    const XY m{__fsub_rn(u, (float)B.tlx), __fsub_rn(v, (float)B.tly)};
+    int val[CH];
+    if (interp == 1) {
+        if (border == 2) sample_linear<CH, true>(I, m, val);
+        else sample_linear<CH, false>(I, m, val);
+    } else {
+        int ix, iy;
+        const bool in = nearest_inside(I, m, ix, iy);
+        if (border == 2) {
+            ix = reflect(ix, I.sw);
+            iy = reflect(iy, I.sh);
+        }
+#pragma unroll
+        for (int c = 0; c < CH; ++c) val[c] = (in || border == 2) ? I.src[(long long)iy * I.spitch + ix * CH + c] : 0;
+    }
+#pragma unroll
+    for (int c = 0; c < CH; ++c) dst[(long long)y * dpitch + x * CH + c] = (uint8_t)val[c];
+}
+
+void launch_warp_backward(const ImageDev& warped, int ch, const float* r_kinv, float scale, int spherical, int tlx, int tly, int interp,
+                          int border, int dw, int dh, uint8_t* dst, long long dpitch, cudaStream_t st)
+{
+    BackwardDev B{};
+    for (int i = 0; i < 9; ++i) B.r_kinv[i] = r_kinv[i];
+    B.scale = scale;
+    B.spherical = spherical;
+    B.tlx = tlx;
+    B.tly = tly;
+    dim3 grid((dw + 31) / 32, (dh + 7) / 8);
+    if (ch == 1) warp_backward_kernel<1><<<grid, 256, 0, st>>>(warped, B, interp, border, dw, dh, dst, dpitch);
+    else warp_backward_kernel<3><<<grid, 256, 0, st>>>(warped, B, interp, border, dw, dh, dst, dpitch);
+    ISB_COUNT_LAUNCH();
 }
 
 void launch_warp_generic(const ImageDev& img, int ch, int interp, int border, uint8_t* dst, long long dpitch,

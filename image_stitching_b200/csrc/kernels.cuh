@@ -48,6 +48,10 @@ inline void launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 block, size
 // RotationWarper::warp: dst(rect_h x rect_w, `ch` channels) from src via the separable-table inverse map.
 void launch_warp_generic(const ImageDev& img, int ch, int interp, int border, uint8_t* dst, long long dpitch,
                          cudaStream_t st);
+// RotationWarper::warpBackward: dst (dw x dh, the original image size) from the warped image `warped` (src / sw / sh / spitch
+// of the descriptor) through the forward map r_kinv = R * K^-1; (tlx, tly) = top-left of the warped ROI
+void launch_warp_backward(const ImageDev& warped, int ch, const float* r_kinv, float scale, int spherical, int tlx, int tly, int interp,
+                          int border, int dw, int dh, uint8_t* dst, long long dpitch, cudaStream_t st);
 // RotationWarper::buildMaps (maps are only ever stored for this diagnostic/parity entry point)
 void launch_build_maps(const ImageDev& img, float* xmap, float* ymap, long long pitch_bytes, cudaStream_t st);
 // BlocksGainCompensator::apply on 8UC3 in place

@@ -136,6 +136,13 @@ ISB_API int isb_warper_warp(isb_warper* w, const uint8_t* src, int src_w, int sr
                             const float K[9], const float R[9], int interp_mode, int border_mode, uint8_t* dst,
                             size_t dst_pitch, int corner_xy[2]);
 
+/* void warpBackward(src, K, R, interp_mode, border_mode, dst_size, dst): the inverse of warp().  src is a warped image of
+ * exactly warpRoi(dst_size) pixels (OpenCV asserts it), dst the original camera frame of dst_w x dst_h pixels.  The
+ * forward map's atan2f / acosf are evaluated per pixel on the device with glibc's float algorithms (bit-identical maps). */
+ISB_API int isb_warper_warp_backward(isb_warper* w, const uint8_t* src, int src_w, int src_h, int channels, size_t src_pitch,
+                                     const float K[9], const float R[9], int interp_mode, int border_mode, int dst_w, int dst_h,
+                                     uint8_t* dst, size_t dst_pitch);
+
 /* ============================================================================================
  * cv::detail::BlocksGainCompensator - apply side only  (image_stitching.cpp:1162).
  * feed() (gain estimation) stays on the reference CPU path; its result enters through set_mat_gains

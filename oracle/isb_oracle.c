@@ -324,6 +324,33 @@ ORC_API void orc_warp(int kind, float scale, const uint8_t* src, int sw, int sh,
     free(ymap);
 }
 
+/* RotationWarperBase::warpBackward: forward map of every pixel of the original frame (libm atan2f / acosf), minus the warped
+ * ROI's top-left, then cv::remap of the warped image.  Returns -1 when src is not warpRoi(dst size) large (CV_Assert). */
+ORC_API int orc_warp_backward(int kind, float scale, const uint8_t* src, int sw, int sh, int ch, size_t spitch, const float* K,
+                              const float* R, int interp, int border, int dw, int dh, uint8_t* dst, size_t dpitch)
+{
+    orc_projector p;
+    int tl[2], br[2];
+    orc_projector_setup(&p, scale, K, R);
+    detect_roi(&p, kind, dw, dh, tl, br);
+    if (br[0] - tl[0] + 1 != sw || br[1] - tl[1] + 1 != sh) return -1;
+    size_t n = (size_t)dw * dh;
+    float* xmap = (float*)malloc(n * sizeof(float));
+    float* ymap = (float*)malloc(n * sizeof(float));
+    for (int y = 0; y < dh; ++y)
+        for (int x = 0; x < dw; ++x) {
+            float u, v;
+            map_forward(&p, kind, (float)x, (float)y, &u, &v);
+            xmap[(size_t)y * dw + x] = u - (float)tl[0];
+            ymap[(size_t)y * dw + x] = v - (float)tl[1];
+        }
+    if (interp == ORC_LINEAR) orc_remap_linear_8u(src, sw, sh, ch, spitch, xmap, ymap, dw, dh, dst, dpitch, border);
+    else orc_remap_nearest_8u(src, sw, sh, ch, spitch, xmap, ymap, dw, dh, dst, dpitch, border);
+    free(xmap);
+    free(ymap);
+    return 0;
+}
+
 /* ---- A.4 dilate 3x3 + resize INTER_LINEAR_EXACT (8UC1) ------------------------------ */
 ORC_API void orc_dilate3x3_8u(const uint8_t* src, int w, int h, uint8_t* dst)
 { /* cv::dilate(src, dst, Mat()): 3x3 rect max; the default border never wins a max */

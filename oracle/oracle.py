@@ -95,6 +95,21 @@ def warp(kind, scale, src, K, R, interp, border):
     return (int(c[0]), int(c[1])), dst
 
 
+def warp_backward(kind, scale, src, K, R, interp, border, dst_size):
+    """RotationWarper::warpBackward: src = warped image (warpRoi(dst_size) large), returns the dst_size = (w, h) frame."""
+    src = np.ascontiguousarray(src)
+    ch = 1 if src.ndim == 2 else src.shape[2]
+    h, w = src.shape[:2]
+    dw, dh = dst_size
+    dst = np.empty((dh, dw) if src.ndim == 2 else (dh, dw, ch), np.uint8)
+    K, R = _f32(K), _f32(R)
+    rc = lib().orc_warp_backward(KIND[kind], C.c_float(scale), _p(src), w, h, ch, C.c_size_t(w * ch), _p(K), _p(R), int(interp),
+                                 int(border), int(dw), int(dh), _p(dst), C.c_size_t(dw * ch))
+    if rc != 0:
+        raise ValueError("src is not warpRoi(dst_size) large")
+    return dst
+
+
 def dilate3x3(m):
     m = np.ascontiguousarray(m, np.uint8)
     o = np.empty_like(m)

@@ -465,6 +465,32 @@ def test_loop_with_simple_blenders(tag):
     assert np.abs(out["result8"].astype(int) - cv8.astype(int)).max() <= MAX_ABS and psnr(out["result8"], cv8) >= MIN_PSNR
 
 
+def test_warp_backward_bit_exact():
+    """isb_warper_warp_backward (RotationWarper::warpBackward, SURVEY.md 8(b)): the forward map's atan2f / acosf run per pixel on
+    the device with glibc's float algorithms (csrc/glibc_math.cuh), so the maps - and with them the resampled frame - are the
+    oracle's (which is pinned against cv2's warpBackward in tests/test_oracle_vs_cv2.py) bit for bit."""
+    for name, div in (("cfg2", 8), ("cfg4", 4), ("cfg3", 16)):
+        rig = synth.make_rig(name, div)
+        for i in (0, 1, rig.n // 2, rig.n - 1):
+            img = synth.make_image(i, rig.W, rig.H)
+            K, R = rig.Ks[i], rig.Rs[i]
+            w = isb.RotationWarper(rig.warp, rig.scale)
+            _, wi = w.warp(img, K, R, isb.INTER_LINEAR, isb.BORDER_REFLECT)
+            _, wm = w.warp(np.full(img.shape[:2], 255, np.uint8), K, R, isb.INTER_NEAREST, isb.BORDER_CONSTANT)
+            for interp, border in ((isb.INTER_LINEAR, isb.BORDER_REFLECT), (isb.INTER_NEAREST, isb.BORDER_CONSTANT),
+                                   (isb.INTER_LINEAR, isb.BORDER_CONSTANT), (isb.INTER_NEAREST, isb.BORDER_REFLECT)):
+                want = orc.warp_backward(rig.warp, rig.scale, wi, K, R, 1 if interp == isb.INTER_LINEAR else 0,
+                                         1 if border == isb.BORDER_REFLECT else 0, (rig.W, rig.H))
+                got = w.warpBackward(wi, K, R, interp, border, (rig.W, rig.H))
+                assert np.array_equal(want, got), (name, i, interp, border)
+            # the mask (8UC1) comes back as the full frame wherever the round trip stays inside the warped ROI
+            back = w.warpBackward(wm, K, R, isb.INTER_NEAREST, isb.BORDER_CONSTANT, (rig.W, rig.H))
+            assert np.array_equal(back, orc.warp_backward(rig.warp, rig.scale, wm, K, R, 0, 0, (rig.W, rig.H)))
+            assert (back == 255).mean() > 0.98
+    with pytest.raises(isb.IsbError):  # CV_Assert on the source size
+        isb.RotationWarper("spherical", 100.0).warpBackward(np.zeros((10, 10), np.uint8), np.eye(3), np.eye(3), 0, 0, (64, 48))
+
+
 @pytest.mark.parametrize("tag", ["feather", "no", "multiband"])
 def test_fused_composer_serves_all_three_blenders(tag):
     """isb_config.use_blend_rule: the C composer applies the reference's own blender set-up (image_stitching.cpp:1173-1193:

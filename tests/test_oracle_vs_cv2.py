@@ -195,3 +195,22 @@ def test_timelapser(cv2_parity):
                 b.process(img, None, c)
                 ref = a.getDst().get()
                 assert ref.shape == b.getDst().shape and np.array_equal(ref, b.getDst()), (ttype, c)
+
+
+def test_warp_backward_matches_cv2(cv2_parity):
+    """RotationWarper::warpBackward (forward map per pixel with libm's atan2f / acosf, then remap)."""
+    cv2 = cv2_parity
+    from oracle import cv_reference as cvr
+    for name, div in (("cfg2", 16), ("cfg4", 8), ("cfg3", 32)):
+        rig = synth.make_rig(name, div)
+        for i in (0, 1, rig.n // 2):
+            img = synth.make_image(i, rig.W, rig.H)
+            w = cvr.make_warper(rig.warp, rig.scale)
+            K, R = rig.Ks[i], rig.Rs[i]
+            _, wi = w.warp(img, K, R, cv2.INTER_LINEAR, cv2.BORDER_REFLECT)
+            for interp, border in ((cv2.INTER_LINEAR, cv2.BORDER_REFLECT), (cv2.INTER_NEAREST, cv2.BORDER_CONSTANT),
+                                   (cv2.INTER_LINEAR, cv2.BORDER_CONSTANT)):
+                want = w.warpBackward(wi, K, R, interp, border, (rig.W, rig.H))
+                got = orc.warp_backward(rig.warp, rig.scale, wi, K, R, 1 if interp == cv2.INTER_LINEAR else 0,
+                                        1 if border == cv2.BORDER_REFLECT else 0, (rig.W, rig.H))
+                assert np.array_equal(want, got), (name, i, interp, border)
