@@ -69,7 +69,8 @@ class Config(C.Structure):
     _fields_ = [("warp_kind", C.c_int), ("warped_image_scale", C.c_float), ("num_bands", C.c_int),
                 ("strip_index", C.c_int), ("strip_count", C.c_int), ("cache_plan", C.c_int), ("async_mode", C.c_int),
                 ("gather_mode", C.c_int), ("pipeline_depth", C.c_int), ("use_blend_rule", C.c_int),
-                ("blend_type", C.c_int), ("blend_strength", C.c_float), ("reserved", C.c_int * 2)]
+                ("blend_type", C.c_int), ("blend_strength", C.c_float), ("compose_scale", C.c_double), ("ingest_rotate", C.c_int),
+                ("reserved", C.c_int * 3)]
 
 
 class _Pano(C.Structure):
@@ -725,7 +726,8 @@ class Composer:
     """The whole compositing loop on the GPU (isb_composer_*)."""
 
     def __init__(self, warp="spherical", scale=1.0, num_bands=5, strip_index=0, strip_count=1, cache_plan=True,
-                 async_mode=False, gather_copy=False, gather_mode=None, pipeline_depth=1, blend_type=None, blend_strength=5.0):
+                 async_mode=False, gather_copy=False, gather_mode=None, pipeline_depth=1, blend_type=None, blend_strength=5.0, ingest_rotate=None,
+                 compose_scale=0.0):
         self.cfg = Config()
         self.cfg.warp_kind = _KIND[warp]
         self.cfg.warped_image_scale = float(scale)
@@ -736,6 +738,9 @@ class Composer:
         # GATHER_PEER_STORES (0) / GATHER_COPY_ENGINE (1) / GATHER_LOCAL (2); gather_copy=True is shorthand for 1
         self.cfg.gather_mode = int(gather_mode) if gather_mode is not None else (GATHER_COPY_ENGINE if gather_copy else GATHER_PEER_STORES)
         self.cfg.pipeline_depth = int(pipeline_depth)
+        # ingest pre-steps inside the composer: images passed to run() are the decoded frames (rotate code as for isb.rotate)
+        self.cfg.ingest_rotate = 0 if ingest_rotate is None else 1 + int(ingest_rotate)
+        self.cfg.compose_scale = float(compose_scale)
         if blend_type is not None:  # the reference's blender set-up (image_stitching.cpp:1173-1193) instead of explicit num_bands
             self.cfg.use_blend_rule = 1
             self.cfg.blend_type = {"no": BLENDER_NO, "feather": BLENDER_FEATHER, "multiband": BLENDER_MULTI_BAND}.get(blend_type, blend_type)

@@ -792,8 +792,8 @@ void Composer::plan(const isb_camera* cams, const int* sizes_wh, int n, int* cor
             ImagePlan& P = img_[i];
             float K[9];
             isb_camera_K(&cams[i], K);
-            P.src_w = sizes_wh[2 * i];
-            P.src_h = sizes_wh[2 * i + 1];
+            // with ingest pre-steps the caller passes decoded sizes; the path works on sz = cvRound(rotated size * compose_scale)
+            ingest_size(sizes_wh[2 * i], sizes_wh[2 * i + 1], P.src_w, P.src_h);
             P.proj.set(cfg_.warp_kind, cfg_.warped_image_scale, K, cams[i].R);
             P.roi = P.proj.warp_roi(P.src_w, P.src_h);
         };
@@ -995,6 +995,11 @@ void Composer::run(const isb_image* imgs, const isb_gainmap* gains, const isb_ma
     if (!planned_) throw Error(ISB_ERR_ASSERT, "Assertion failed: isb_composer_plan() must precede isb_composer_run()");
     if (!imgs || !out) throw Error(ISB_ERR_NULL_PTR, "imgs/out are null");
     ISB_ASSERT(n == (int)img_.size());
+    std::vector<isb_image> ingested;
+    if (ingest_active()) {
+        ingest(imgs, n, ingested, current_stream());
+        imgs = ingested.data();
+    }
     if (eff_blend_type_ != ISB_BLENDER_MULTI_BAND) {
         run_simple(imgs, gains, seams, n, out);
         return;
@@ -1248,6 +1253,82 @@ void Composer::run(const isb_image* imgs, const isb_gainmap* gains, const isb_ma
     for (int i = 0; i < n && !any_host; ++i)
         if (!tiles_of_image_[i].empty() && mem_kind(imgs[i].data) == MemKind::Host) any_host = true;
     if (any_host && !cfg_.async_mode) ISB_CUDA(cudaStreamSynchronize(st));
+}
+
+// ---- ingest pre-steps of the loop (image_stitching.cpp:1093-1103, 1143-1146) inside the composer -------------------------
+bool Composer::ingest_active() const
+{
+    return cfg_.ingest_rotate != 0 || (cfg_.compose_scale > 0 && std::abs(cfg_.compose_scale - 1) > 1e-1);
+}
+
+void Composer::ingest_size(int w, int h, int& ow, int& oh) const
+{
+    ISB_ASSERT(cfg_.ingest_rotate >= 0 && cfg_.ingest_rotate <= 2);
+    int rw = w, rh = h;
+    if (cfg_.ingest_rotate == 1 + ISB_ROTATE_90_CLOCKWISE) { rw = h; rh = w; }
+    ow = rw;
+    oh = rh;
+    if (cfg_.compose_scale > 0 && std::abs(cfg_.compose_scale - 1) > 1e-1) {  // :1130-1133 / cv::resize(Size(), fx, fy): cvRound
+        ow = (int)std::nearbyint(rw * cfg_.compose_scale);
+        oh = (int)std::nearbyint(rh * cfg_.compose_scale);
+    }
+}
+
+void Composer::ingest(const isb_image* imgs, int n, std::vector<isb_image>& out, cudaStream_t st)
+{
+    const bool scale = cfg_.compose_scale > 0 && std::abs(cfg_.compose_scale - 1) > 1e-1;
+    out.assign(imgs, imgs + n);
+    ing_out_.begin();
+    ing_tab_.begin();
+    std::vector<size_t> off(n), toff(n);
+    for (int i = 0; i < n; ++i) {
+        off[i] = ing_out_.take((size_t)img_[i].src_w * 3 * img_[i].src_h + 32);
+        toff[i] = ing_tab_.take((size_t)(img_[i].src_w + img_[i].src_h) * sizeof(uint32_t));
+    }
+    char* ob = ing_out_.commit();
+    char* tb = ing_tab_.commit();
+    std::vector<uint32_t> tx, ty;
+    for (int i = 0; i < n; ++i) {
+        const isb_image& im = imgs[i];
+        if (!im.data) throw Error(ISB_ERR_NULL_PTR, "image data is null");
+        ISB_ASSERT(im.width > 0 && im.height > 0 && im.pitch >= (size_t)im.width * 3);
+        int ew, eh;
+        ingest_size(im.width, im.height, ew, eh);
+        ISB_ASSERT(ew == img_[i].src_w && eh == img_[i].src_h);  // the decoded size the plan was made for
+        const uint8_t* cur = im.data;
+        size_t cp = im.pitch;
+        int cw = im.width, chh = im.height;
+        if (mem_kind(cur) != MemKind::Device) {
+            const size_t rb = (size_t)cw * 3;
+            uint8_t* up = static_cast<uint8_t*>(ing_up_.ensure(rb * chh));
+            copy2d(up, rb, cur, cp, rb, chh, st);
+            cur = up;
+            cp = rb;
+        }
+        uint8_t* dst = reinterpret_cast<uint8_t*>(ob + off[i]);
+        if (cfg_.ingest_rotate) {
+            const int code = cfg_.ingest_rotate - 1;
+            const int rw = code == ISB_ROTATE_90_CLOCKWISE ? chh : cw, rh = code == ISB_ROTATE_90_CLOCKWISE ? cw : chh;
+            uint8_t* r = scale ? static_cast<uint8_t*>(ing_rot_.ensure((size_t)rw * 3 * rh)) : dst;
+            launch_rotate(cur, cw, chh, 3, (long long)cp, code, r, (long long)rw * 3, st);
+            cur = r;
+            cp = (size_t)rw * 3;
+            cw = rw;
+            chh = rh;
+        }
+        if (scale) {
+            build_linear_exact_table(cw, ew, tx, cfg_.compose_scale);
+            build_linear_exact_table(chh, eh, ty, cfg_.compose_scale);
+            uint32_t* t = reinterpret_cast<uint32_t*>(tb + toff[i]);
+            ISB_CUDA(cudaMemcpyAsync(t, tx.data(), tx.size() * 4, cudaMemcpyHostToDevice, st));
+            ISB_CUDA(cudaMemcpyAsync(t + tx.size(), ty.data(), ty.size() * 4, cudaMemcpyHostToDevice, st));
+            launch_resize_exact(cur, cw, chh, 3, (long long)cp, t, t + tx.size(), dst, ew, eh, (long long)ew * 3, st);
+        }
+        out[i].data = dst;
+        out[i].width = ew;
+        out[i].height = eh;
+        out[i].pitch = (size_t)ew * 3;
+    }
 }
 
 // Blender::NO / FeatherBlender (image_stitching.cpp:1086-1229 with blend_type no / feather): the loop call by call, every

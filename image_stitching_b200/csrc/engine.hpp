@@ -249,6 +249,12 @@ public:
     int effective_num_bands() const { return eff_num_bands_; }
     float effective_sharpness() const { return eff_sharpness_; }
 private:
+    // ingest pre-steps (rotate + compose-scale resize) on the device: returns device-resident stand-ins of `imgs`
+    bool ingest_active() const;
+    void ingest_size(int w, int h, int& ow, int& oh) const;
+    void ingest(const isb_image* imgs, int n, std::vector<isb_image>& out, cudaStream_t st);
+    Arena ing_out_, ing_tab_;
+    DevBuf ing_up_, ing_rot_;
     void run_simple(const isb_image* imgs, const isb_gainmap* gains, const isb_mask* seams, int n, isb_pano* out);
     int eff_blend_type_ = ISB_BLENDER_MULTI_BAND, eff_num_bands_ = 0;
     float eff_sharpness_ = 0.02f;

@@ -133,6 +133,13 @@ def seam_source_mask(W: int, H: int) -> np.ndarray:
     return m
 
 
+def seam_band_mask(w: int, h: int) -> np.ndarray:
+    """w x h source-space mask: 255 in the central 75 % of the columns (a stand-in for the seam finder's output)."""
+    m = np.zeros((h, w), dtype=np.uint8)
+    m[:, int(round(w * 0.125)):int(round(w * 0.875))] = 255
+    return m
+
+
 def seam_camera(K: np.ndarray, scale: np.float32):
     """K and warper scale at seam resolution (image_stitching.cpp:973-983: focal, ppx, ppy
     scaled by seam_work_aspect; warper created with warped_image_scale * seam_work_aspect)."""
@@ -143,3 +150,29 @@ def seam_camera(K: np.ndarray, scale: np.float32):
     Ks[1, 1] *= a
     Ks[1, 2] *= a
     return Ks, np.float32(np.float32(scale) * a)
+
+
+def default_flow_setup(rig: Rig, compose_megapix: float = 0.4, seam_megapix: float = 0.1):
+    """Scalars and cameras of the reference's DEFAULT invocation (image_stitching.cpp:53-55: work_megapix = -1, seam_megapix =
+    0.1, compose_megapix = 0.4) for a rig of full-size frames: compose_scale (:1107-1108), the compose-scale cameras and warper
+    scale (:1115-1127), the seam-scale cameras and warper scale (:973-983) and the compose size sz (:1130-1133)."""
+    W, H = rig.W, rig.H
+    compose_scale = min(1.0, math.sqrt(compose_megapix * 1e6 / (W * H)))
+    seam_scale = min(1.0, math.sqrt(seam_megapix * 1e6 / (W * H)))
+    work_aspect, seam_aspect = compose_scale / 1.0, seam_scale / 1.0  # work_scale = 1
+    scale_c = np.float32(rig.scale) * np.float32(work_aspect)
+    Kc, Ks = [], []
+    for K in rig.Ks:
+        Kd = np.eye(3)
+        for (r, c) in ((0, 0), (1, 1), (0, 2), (1, 2)):
+            Kd[r, c] = float(K[r, c]) * work_aspect
+        Kc.append(Kd.astype(np.float32))
+        Km = K.copy()
+        swa = np.float32(seam_aspect)
+        for (r, c) in ((0, 0), (0, 2), (1, 1), (1, 2)):
+            Km[r, c] *= swa
+        Ks.append(Km)
+    rnd = lambda v: int(np.rint(v))  # noqa: E731  (cvRound)
+    return dict(compose_scale=compose_scale, seam_scale=seam_scale, scale_c=scale_c, Kc=Kc, Ks=Ks,
+                seam_warper_scale=np.float32(float(rig.scale) * seam_aspect), sz=(rnd(W * compose_scale), rnd(H * compose_scale)),
+                seam_size=(rnd(W * seam_scale), rnd(H * seam_scale)))

@@ -283,7 +283,14 @@ typedef struct isb_config {
                                  with the per-call kernels; strips and pipeline_depth apply to MULTI_BAND only. */
     int blend_type;           /* ISB_BLENDER_NO / ISB_BLENDER_FEATHER / ISB_BLENDER_MULTI_BAND (blend_type, image_stitching.cpp:80) */
     float blend_strength;     /* blend_strength, image_stitching.cpp:81 (default 5) */
-    int reserved[2];
+    double compose_scale;     /* ingest pre-steps of the loop inside the composer: when ingest_rotate != 0 or
+                                 |compose_scale - 1| > 0.1 the isb_image arguments are the DECODED frames; every run first applies
+                                 cv::rotate (image_stitching.cpp:1093-1103) and cv::resize(Size(), compose_scale, compose_scale,
+                                 INTER_LINEAR_EXACT) (:1143-1146) on the device and warps the result.  isb_composer_plan() then
+                                 takes the decoded sizes and derives sz = cvRound(rotated size * compose_scale) (:1130-1133); the
+                                 cameras are the compose-scale ones (:1123-1125).  0 or 1: no resize. */
+    int ingest_rotate;        /* 0: none; 1 + ISB_ROTATE_90_CLOCKWISE (portrait frames) or 1 + ISB_ROTATE_180 (:1093-1103) */
+    int reserved[3];
 } isb_config;
 
 /* Output of isb_compose: the panorama (dst_roi_final_ size).  data/mask describe the FULL panorama buffer

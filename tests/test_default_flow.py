@@ -85,15 +85,17 @@ def default_flow(rotate180, resize_fx, warp_nearest, warp_roi, compose, div=2, n
     x1 = max(r[0] + r[2] for r in rois); y1 = max(r[1] + r[3] for r in rois)
     nb = reference_num_bands(x1 - x0, y1 - y0)
     # pixels: rotate + resize (:1093-1103, :1143-1146)
-    rotated, resized = [], []
+    rotated, resized, fulls = [], [], []
     for i in range(rig.n):
         full = synth.make_image(i, W, H)
+        fulls.append(full)
         r = rotate180(full)
         rotated.append(r)
         resized.append(resize_fx(r, compose_scale))
         assert resized[-1].shape[:2] == (sz[1], sz[0])
     out = compose(resized, Kc, rig.Rs, scale_c, rig.warp, nb, gains, seams)
-    return dict(rig=rig, nb=nb, rois=rois, seams=seams, rotated=rotated, resized=resized, out=out, sz=sz, scale_c=scale_c)
+    return dict(rig=rig, nb=nb, rois=rois, seams=seams, rotated=rotated, resized=resized, out=out, sz=sz, scale_c=scale_c,
+                fulls=fulls, Kc=Kc, gains=gains, compose_scale=compose_scale)
 
 
 def oracle_flow(**kw):
@@ -190,3 +192,32 @@ def test_default_flow_gpu_vs_oracle():
     ref = oracle_flow()
     dmax, exact16 = assert_same_flow(got, ref)
     assert dmax == 0 and exact16
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("blend", ["rule", "explicit"])
+def test_default_flow_one_call_from_decoded_frames(blend):
+    """the ingest pre-steps inside the composer.  isb_composer_run() takes the DECODED frames, applies
+    rotate(ROTATE_180) and the compose-scale INTER_LINEAR_EXACT resize on the device and warps the result - the reference's
+    default flow in one call, bit-exact against the oracle flow.  `rule`: the band count comes from the reference's own blender
+    set-up (image_stitching.cpp:1173-1193) as well."""
+    import image_stitching_b200 as isb
+    ref = oracle_flow()
+    rig = ref["rig"]
+    kw = dict(blend_type="multiband", blend_strength=BLEND_STRENGTH) if blend == "rule" else {}
+    c = isb.Composer(rig.warp, ref["scale_c"], ref["nb"] if blend == "explicit" else 0, ingest_rotate=isb.ROTATE_180,
+                     compose_scale=ref["compose_scale"], **kw)
+    cams = isb.cameras_from_KR(ref["Kc"], rig.Rs)
+    corners, sizes, roi = c.plan(cams, [(rig.W, rig.H)] * rig.n)  # decoded sizes
+    assert [tuple(r) for r in ref["rois"]] == [(cx, cy, w, h) for (cx, cy), (w, h) in zip(corners, sizes)]
+    out = c.run(ref["fulls"], ref["gains"], ref["seams"], want16=True)
+    assert tuple(out["dst_roi"]) == tuple(ref["out"]["dst_roi"])
+    assert np.array_equal(out["mask"], ref["out"]["mask"]) and np.array_equal(out["result16"], ref["out"]["result16"])
+    # portrait frames: ROTATE_90_CLOCKWISE swaps the frame's sides before the resize
+    c90 = isb.Composer(rig.warp, ref["scale_c"], ref["nb"], ingest_rotate=isb.ROTATE_90_CLOCKWISE, compose_scale=ref["compose_scale"])
+    tall = [np.ascontiguousarray(np.rot90(f, 1)) for f in ref["fulls"]]  # rotating these clockwise gives the landscape frames
+    c90.plan(cams, [(rig.H, rig.W)] * rig.n)
+    out90 = c90.run(tall, ref["gains"], ref["seams"], want16=True)
+    want = orc.compose([orc.resize_linear_exact_ex(orc.rotate(t, 0), ref["sz"][0], ref["sz"][1], ref["compose_scale"], ref["compose_scale"])
+                        for t in tall], ref["Kc"], rig.Rs, ref["scale_c"], rig.warp, ref["nb"], ref["gains"], ref["seams"])
+    assert np.array_equal(out90["mask"], want["mask"]) and np.array_equal(out90["result16"], want["result16"])
