@@ -78,8 +78,9 @@ struct alignas(16) CellTile {
     int pitch0, pitch1;   // elements (a packed tile's weight plane has the pitch of its pixel plane)
     int ox, oy;           // tile origin at level l
     int wc, hc;           // size of level l + 1
+    int tile, pad[3];     // tile index (selects the tensor map of its level l + 1 plane in the TMA-staged cell kernel)
 };
-static_assert(sizeof(CellTile) == 48, "kernel 3 moves a record as three 16-byte words");
+static_assert(sizeof(CellTile) == 64, "kernel 3 moves a record as four 16-byte words");
 
 // Destination state of one blend (MultiBandBlender::prepare)
 struct DstDev {
@@ -96,6 +97,12 @@ struct DstDev {
     int row0, row1;            // level-0 rows [row0,row1) this process owns (strip)
     int packed0;               // all tiles carry the byte-packed level 0 (fused composer)
     int max_cell_tiles;        // longest tile list of any macro cell
+    // TMA-staged cell kernel: tensor maps (CUtensorMap, device memory) of the packed level-l planes of every tile,
+    // tmap_tiles[l * n_tiles + tile] (l = 1..nb; box 24 x 18 pixels), and of the collapsed levels C[l], tmap_c[l] (viewed as
+    // uint32 pairs; box 40 x 18 words).  nullptr: the driver has no tensor-map encoder, the LDG kernels are used.
+    const void* tmap_tiles;
+    const void* tmap_c;
+    int n_tiles;
 };
 
 struct OutDev {

@@ -350,11 +350,47 @@ void PyramidEngine::blend(const OutDev& out, cudaStream_t st)
                     ISB_ASSERT(T.wpitch[l] == T.ppitch[l]);
                     c.ox = T.x0 >> l; c.oy = T.y0 >> l;
                     c.wc = T.w >> (l + 1); c.hc = T.h >> (l + 1);
+                    c.tile = list[e];
                 }
             CellTile* dd = static_cast<CellTile*>(cdesc_dev_.ensure(desc.size() * sizeof(CellTile)));
             ISB_CUDA(cudaMemcpyAsync(dd, desc.data(), desc.size() * sizeof(CellTile), cudaMemcpyHostToDevice, st));
             ISB_CUDA(cudaStreamSynchronize(st));  // `desc` is a local
             dst_.cdesc = dd;
+            // tensor maps of the TMA-staged cell kernel: level l planes of every tile (l = 1..nb) and the collapsed levels
+            dst_.tmap_tiles = dst_.tmap_c = nullptr;
+            dst_.n_tiles = (int)tiles_.size();
+            if (encode_tiled_fn() && nb >= 5) {
+                const size_t nt = tiles_.size();
+                std::vector<CUtensorMap> maps((size_t)(nb + 1) * nt + (nb + 1));
+                std::memset(maps.data(), 0, maps.size() * sizeof(CUtensorMap));
+                bool ok = true;
+                const cuuint32_t estr[2] = {1, 1};
+                for (int l = 1; ok && l <= nb; ++l) {
+                    for (size_t t = 0; ok && t < nt; ++t) {
+                        const TileDev& T = tiles_[t];
+                        const cuuint64_t dims[2] = {(cuuint64_t)(T.w >> l), (cuuint64_t)(T.h >> l)};
+                        const cuuint64_t strides[1] = {(cuuint64_t)T.ppitch[l] * sizeof(uint32_t)};
+                        const cuuint32_t box[2] = {24, 18};
+                        ok = encode_tiled_fn()(&maps[(size_t)l * nt + t], CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, T.P[l], dims, strides, box, estr,
+                                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+                    }
+                    if (!ok) break;
+                    const cuuint64_t dims[2] = {(cuuint64_t)2 * (dst_.pw >> l), (cuuint64_t)(dst_.ph >> l)};
+                    const cuuint64_t strides[1] = {(cuuint64_t)dst_.cpitch[l] * sizeof(uint2)};
+                    const cuuint32_t box[2] = {40, 18};
+                    ok = encode_tiled_fn()(&maps[(size_t)(nb + 1) * nt + l], CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, dst_.C[l], dims, strides, box, estr,
+                                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+                }
+                if (ok) {
+                    CUtensorMap* md = static_cast<CUtensorMap*>(tmaps_blend_dev_.ensure(maps.size() * sizeof(CUtensorMap)));
+                    ISB_CUDA(cudaMemcpyAsync(md, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, st));
+                    ISB_CUDA(cudaStreamSynchronize(st));  // `maps` is a local
+                    dst_.tmap_tiles = md;
+                    dst_.tmap_c = md + (size_t)(nb + 1) * nt;
+                }
+            }
         }
     }
     for (int l = nb; l >= 0; --l) {

@@ -120,7 +120,7 @@ private:
     int committed_ = 0;           // tiles [0, committed_) have storage
     Arena arena_;                 // fused path: one block for all tiles
     std::vector<DevBuf*> extra_;  // classic path: one allocation per late-added tile
-    DevBuf tiles_dev_, warp_work_dev_, down_work_dev_, cells_dev_, cdesc_dev_, dst_buf_, tmaps_dev_;
+    DevBuf tiles_dev_, warp_work_dev_, down_work_dev_, cells_dev_, cdesc_dev_, dst_buf_, tmaps_dev_, tmaps_blend_dev_;
     bool last_fast_ = false;
     bool use_tma_ = false;  // level 0 -> 1 pyrDown staged by TMA (packed tiles large enough for a full box)
     std::vector<WorkItem> warp_work_;
