@@ -284,9 +284,11 @@ def measure(name, div, args, rank, world, dev, stream, full):
     d_imgs = [torch.from_numpy(im).to(dev) for im in imgs] if imgs is not None else torch_images(rig, dev)
     d_gains = [torch.from_numpy(g).to(dev) for g in gains]
     d_seams = [torch.from_numpy(s).to(dev) for s in seams]
-    m_ = 1 << rig.nb  # the rigs' band counts are below the prepare() clamp, so nb is the actual band count
-    padded_h = (ph + m_ - 1) // m_ * m_
-    all_rows = strips.all_strip_rows(padded_h, ph, rig.nb, world)
+    # every rank's rows (the planner balances the cuts by work; identical on all ranks, gathered here for the NCCL path)
+    all_rows = [comp.planned_rows()]
+    if world > 1:
+        all_rows = [None] * world
+        dist.all_gather_object(all_rows, comp.planned_rows())
 
     # ---- the panorama(s) on rank 0 ----------------------------------------------------------------------------------
     peer = mode in ("p2p", "copy")
@@ -374,7 +376,7 @@ def measure(name, div, args, rank, world, dev, stream, full):
     ms_step = ms_total / steps
     res = {"rig": rig, "roi": roi, "ms_step": ms_step, "value": out_mp * steps / (ms_total / 1e3), "steps": steps, "plan_s": plan_s,
            "launches_per_step": int(launches_per_step), "clocks": clk.summary(), "gather": mode, "out_mp": out_mp,
-           "steps_in_flight": depth}
+           "steps_in_flight": depth, "strip_rows": [list(r) for r in all_rows]}
     free, total = torch.cuda.mem_get_info(dev)
     res["device_mem_used_gb"] = (total - free) / 1e9  # includes the library's own cudaMalloc blocks (not torch's)
 
@@ -727,6 +729,7 @@ def run_ours(args, rank, world):
                 "dtype": "u8/s16/f32", "data": "synthetic", "config": config_of(rig, args.workload, args.div, roi),
                 "latency_ms_per_step": res["latency_ms_per_step"],
                 "layout": {"parallelism": par, "plan_cache": True, "plan_s": res["plan_s"], "steps_in_flight": res["steps_in_flight"],
+                           "strip_rows": res["strip_rows"],
                            "steps_in_flight_note": "ms_per_step / value are the throughput of back-to-back steps with that many "
                                                    "runs in flight (own pyramids and panorama each); latency_ms_per_step is one "
                                                    "step at a time",
@@ -741,7 +744,7 @@ def run_ours(args, rank, world):
             rl = roofline_of(sub, world, "cfg3")
             line["cfg3"] = {"config": config_of(sub["rig"], "cfg3", 1, sub["roi"]), "value": sub["value"], "unit": UNIT,
                             "ms_per_step": sub["ms_step"], "latency_ms_per_step": sub["latency_ms_per_step"], "steps": sub["steps"],
-                            "steps_in_flight": sub["steps_in_flight"], "parallelism": f"strips{world}" + ("" if world == 1 else f"+{sub['gather']}-gather"),
+                            "steps_in_flight": sub["steps_in_flight"], "strip_rows": sub["strip_rows"], "parallelism": f"strips{world}" + ("" if world == 1 else f"+{sub['gather']}-gather"),
                             "roofline_frac": rl["frac"], "algorithmic_bytes_per_step": rl["algorithmic_bytes_per_step"],
                             "stages_ms": sub["stages_ms"], "parity": sub["parity"], "plan_s": sub["plan_s"],
                             "device_mem_used_gb_rank0": sub["device_mem_used_gb"],

@@ -835,6 +835,12 @@ class Composer:
             _chk(n)
         return {lib().isb_composer_stage_name(i).decode(): float(ms[i]) for i in range(n)}
 
+    def planned_rows(self):
+        """Rows (y0, y1) of the panorama this composer's strip covers (valid after plan())."""
+        a, b = C.c_int(0), C.c_int(0)
+        _chk(lib().isb_composer_strip_rows(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def source_band(self, index):
         """Rows [lo, hi] of source image `index` this strip reads (strip-sharded plans; the whole image otherwise)."""
         lo, hi = C.c_int(0), C.c_int(0)

@@ -485,6 +485,13 @@ int isb_composer_source_band(isb_composer* c, int index, int* lo, int* hi)
         if (hi) *hi = b[2 * index + 1];
     });
 }
+int isb_composer_strip_rows(isb_composer* c, int* y0, int* y1)
+{
+    return guarded([&] {
+        NOT_NULL(c); NOT_NULL(y0); NOT_NULL(y1);
+        c->impl.first().planned_rows(*y0, *y1);
+    });
+}
 long long isb_composer_last_h2d_bytes(isb_composer* c) { return c ? (long long)c->impl.last().last_h2d_bytes() : 0; }
 int isb_compose(const isb_image* imgs, const isb_camera* cams, const isb_gainmap* gains, const isb_mask* seams, int n,
                 const isb_config* cfg, isb_pano* out)

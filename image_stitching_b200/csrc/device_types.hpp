@@ -103,6 +103,7 @@ struct DstDev {
     const void* tmap_tiles;
     const void* tmap_c;
     int n_tiles;
+    int tmap_level0;           // tmap_tiles[0 * n_tiles + tile] holds the level-0 planes too (box 32 x 32): the pipelined level-0 kernel applies
 };
 
 struct OutDev {

@@ -365,6 +365,17 @@ void PyramidEngine::blend(const OutDev& out, cudaStream_t st)
                 std::memset(maps.data(), 0, maps.size() * sizeof(CUtensorMap));
                 bool ok = true;
                 const cuuint32_t estr[2] = {1, 1};
+                bool ok0 = true;  // level-0 planes, 32 x 32 boxes (the pipelined level-0 kernel)
+                for (size_t t = 0; ok0 && t < nt; ++t) {
+                    const TileDev& T = tiles_[t];
+                    const cuuint64_t dims[2] = {(cuuint64_t)T.w, (cuuint64_t)T.h};
+                    const cuuint64_t strides[1] = {(cuuint64_t)T.ppitch[0] * sizeof(uint32_t)};
+                    const cuuint32_t box[2] = {32, 32};
+                    ok0 = T.w >= 32 && T.h >= 32 &&
+                          encode_tiled_fn()(&maps[t], CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, T.P[0], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+                }
+                dst_.tmap_level0 = ok0 ? 1 : 0;
                 for (int l = 1; ok && l <= nb; ++l) {
                     for (size_t t = 0; ok && t < nt; ++t) {
                         const TileDev& T = tiles_[t];
@@ -883,12 +894,8 @@ void Composer::plan(const isb_camera* cams, const int* sizes_wh, int n, int* cor
         // and the Laplacian at row q additionally level l + 1 rows q/2 - 1 .. q/2 + 1.  The extremes are reached at the top
         // level: rows [y0 - 4 m + 2, y1 + 3 m - 2).  So the halo is FOUR cells above and THREE cells below the strip; data
         // beyond it - and the artificial border rules at the cuts - cannot reach an owned row.
-        int y0, y1;
-        strip_rows(g.roi.h, g.nb, cfg_.strip_index, cfg_.strip_count, y0, y1);
-        const int m = 1 << g.nb;
-        const int halo_top = cfg_.strip_count > 1 ? 4 * m : 0, halo_bot = cfg_.strip_count > 1 ? 3 * m : 0;
-        const int sy0 = std::max(0, y0 - halo_top), sy1 = std::min(g.roi.h, (y1 + m - 1) / m * m + halo_bot);
-        eng_.reset(g, sy0, std::max(sy1 - sy0, 0), y0, y1, /*packed=*/true);
+        // (the cuts themselves are chosen below, once the work per cell row is known)
+        eng_.reset(g, 0, g.roi.h, 0, g.roi.h, /*packed=*/true);  // geometry only; re-issued with the strip's rows before tiles are added
 
         // separable trig tables (every image) + slots for the per-run coefficient tables
         tables_.begin();
@@ -968,6 +975,8 @@ void Composer::plan(const isb_camera* cams, const int* sizes_wh, int n, int* cor
         }
         tiles_of_image_.assign(n, {});
         const int kDilate = 4;
+        struct RectSpec { int img, X0, Y0, W, H; };  // level-0 pixels, padded-panorama coordinates, on the 2^nb grid
+        std::vector<RectSpec> rects;
         for (int i = 0; i < n; ++i) {
             const int cw = full[i].W >> g.nb, chh = full[i].H >> g.nb;
             const uint8_t* o = occ.data() + occ_tiles[i].occ_off;
@@ -988,12 +997,79 @@ void Composer::plan(const isb_camera* cams, const int* sizes_wh, int n, int* cor
                     lo = std::min(lo, col_lo[x1]);
                     hi = std::max(hi, col_hi[x1]);
                 }
-                const int t = eng_.add_rect(i, full[i].X0 + (cx << g.nb), full[i].Y0 + (lo << g.nb), (x1 - cx + 1) << g.nb,
-                                            (hi - lo + 1) << g.nb, img_[i].roi.x, img_[i].roi.y, img_[i].roi.w, img_[i].roi.h,
-                                            need_dev_.as<uint32_t>() + occ_tiles[i].occ_off, full[i].X0, full[i].Y0, cw);
-                if (t >= 0) tiles_of_image_[i].push_back(t);
+                rects.push_back(RectSpec{i, full[i].X0 + (cx << g.nb), full[i].Y0 + (lo << g.nb), (x1 - cx + 1) << g.nb, (hi - lo + 1) << g.nb});
                 cx = x1 + 1;
             }
+        }
+        // Strip cuts, balanced by WORK.  Per cell row: W[r] = cells of all pyramid rectangles in that row (kernels 1 and 2 and
+        // the coarse blend levels scale with it), and the level-0 blend scales with the panorama width.  A strip [a, b) of cell
+        // rows warps rows [a - 4, b + 3) and blends rows [a, b); the cuts minimise the largest strip cost (greedy partition
+        // under a bisected bound).  Every rank evaluates the same integers, so every rank finds the same cuts.
+        int y0 = 0, y1 = g.roi.h;
+        const int m = 1 << g.nb;
+        if (cfg_.strip_count > 1) {
+            const int cells_y = g.roi.h >> g.nb, cells_x = g.roi.w >> g.nb, N = cfg_.strip_count;
+            strip_rows(g.roi.h, g.nb, cfg_.strip_index, N, y0, y1);  // arithmetic cuts: the fall-back for very short panoramas
+            if (cells_y >= 2 * N + 7) {
+                std::vector<double> PW(cells_y + 1, 0.0);
+                {
+                    std::vector<double> Wr(cells_y, 0.0);
+                    for (const RectSpec& r : rects)
+                        for (int cy = r.Y0 >> g.nb; cy < (r.Y0 + r.H) >> g.nb; ++cy) Wr[cy] += (double)(r.W >> g.nb);
+                    for (int r = 0; r < cells_y; ++r) PW[r + 1] = PW[r] + Wr[r];
+                }
+                const double alpha = 0.85, beta = 1.0;
+                auto cost = [&](int a, int b) {
+                    const int ha = a == 0 ? 0 : std::max(0, a - 4), hb = b == cells_y ? cells_y : std::min(cells_y, b + 3);
+                    return alpha * (PW[hb] - PW[ha]) + beta * (double)cells_x * (b - a);
+                };
+                auto partition = [&](double T, std::vector<int>* cuts) {  // greedy: strips as long as the bound allows
+                    int a = 0, k = 0;
+                    if (cuts) cuts->assign(1, 0);
+                    while (a < cells_y) {
+                        int b = a + 1;
+                        if (cost(a, b) > T) return N + 1;  // a single row exceeds the bound
+                        while (b < cells_y && cost(a, b + 1) <= T) ++b;
+                        // leave at least one row for each of the remaining strips
+                        b = std::min(b, cells_y - (N - 1 - k));
+                        b = std::max(b, a + 1);
+                        if (cuts) cuts->push_back(b);
+                        a = b;
+                        ++k;
+                        if (k > N) return k;
+                    }
+                    return k;
+                };
+                double lo_t = 0.0, hi_t = cost(0, cells_y);
+                for (int it = 0; it < 60; ++it) {
+                    const double mid = 0.5 * (lo_t + hi_t);
+                    if (partition(mid, nullptr) <= N) hi_t = mid;
+                    else lo_t = mid;
+                }
+                std::vector<int> cuts;
+                if (partition(hi_t, &cuts) <= N) {
+                    while ((int)cuts.size() < N + 1) {  // fewer strips than ranks: split the tallest strip
+                        int best = 0;
+                        for (int k = 1; k + 1 < (int)cuts.size(); ++k)
+                            if (cuts[k + 1] - cuts[k] > cuts[best + 1] - cuts[best]) best = k;
+                        if (cuts[best + 1] - cuts[best] < 2) break;
+                        cuts.insert(cuts.begin() + best + 1, (cuts[best] + cuts[best + 1]) / 2);
+                    }
+                    if ((int)cuts.size() == N + 1) {
+                        y0 = cuts[cfg_.strip_index] << g.nb;
+                        y1 = cuts[cfg_.strip_index + 1] << g.nb;
+                    }
+                }
+            }
+        }
+        const int halo_top = cfg_.strip_count > 1 ? 4 * m : 0, halo_bot = cfg_.strip_count > 1 ? 3 * m : 0;
+        const int sy0 = std::max(0, y0 - halo_top), sy1 = std::min(g.roi.h, (y1 + m - 1) / m * m + halo_bot);
+        eng_.reset(g, sy0, std::max(sy1 - sy0, 0), y0, y1, /*packed=*/true);
+        for (const RectSpec& r : rects) {
+            const int i = r.img;
+            const int t = eng_.add_rect(i, r.X0, r.Y0, r.W, r.H, img_[i].roi.x, img_[i].roi.y, img_[i].roi.w, img_[i].roi.h,
+                                        need_dev_.as<uint32_t>() + occ_tiles[i].occ_off, full[i].X0, full[i].Y0, full[i].W >> g.nb);
+            if (t >= 0) tiles_of_image_[i].push_back(t);
         }
         eng_.commit_tiles(st);
         // strip-sharded runs: the band of source rows this strip can read from every image (host sources are uploaded

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdint>
 #include <stdexcept>
 #include <string>
@@ -294,6 +295,13 @@ private:
 public:
     ~Composer();
     size_t last_h2d_bytes() const { return h2d_bytes_; }
+    // rows [y0, y1) of the final panorama this (strip-sharded) composer produces; valid after plan()
+    void planned_rows(int& y0, int& y1) const
+    {
+        const int fh = eng_.geom().roi_final.h;
+        y0 = std::min(eng_.own_y0(), fh);
+        y1 = std::min(eng_.own_y1(), fh);
+    }
     const std::vector<int>& src_band() const { return src_band_; }
 };
 

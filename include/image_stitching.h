@@ -327,6 +327,10 @@ ISB_API int isb_composer_byte_model(isb_composer* c, double* S_px, double* M_px,
  * source bytes the last isb_composer_run() copied host -> device */
 ISB_API int isb_composer_source_band(isb_composer* c, int index, int* row_lo, int* row_hi);
 ISB_API long long isb_composer_last_h2d_bytes(isb_composer* c);
+/* rows [y0, y1) of the panorama this composer's strip covers (after isb_composer_plan).  The planner cuts the panorama on the
+ * 2^nb grid so that every strip has about the same WORK (pyramid area incl. halo + blended rows), which differs from the
+ * plain arithmetic cuts of isb_strip_rows() whenever the images are not spread evenly over the rows. */
+ISB_API int isb_composer_strip_rows(isb_composer* c, int* y0, int* y1);
 /* one-shot convenience == create + plan + run + destroy */
 ISB_API int isb_compose(const isb_image* imgs, const isb_camera* cams, const isb_gainmap* gains, const isb_mask* seam_masks,
                         int n, const isb_config* cfg, isb_pano* out);
@@ -357,7 +361,8 @@ ISB_API int isb_ipc_close_handle(void* dev_ptr);
 /* cudaMemcpyAsync(cudaMemcpyDefault) on the library's stream, for moving results out of such buffers */
 ISB_API int isb_memcpy(void* dst, const void* src, size_t bytes, int synchronize);
 
-/* Strip planner (multi-GPU): rows [y0,y1) of the padded panorama owned by strip i of n, boundaries on the 2^nb grid */
+/* Arithmetic strip cuts (rows [y0,y1) of strip i of n, boundaries on the 2^nb grid, halo-aware): what the planner falls back
+ * to for very short panoramas; the rows a composer actually produces are isb_composer_strip_rows() / isb_pano.strip_y0/1 */
 ISB_API int isb_strip_rows(int padded_h, int final_h, int num_bands, int strip_index, int strip_count, int* y0, int* y1);
 
 #ifdef __cplusplus
