@@ -260,7 +260,7 @@ def measure(name, div, args, rank, world, dev, stream, full):
     from image_stitching_b200 import strips
 
     local = dev.index
-    rig, imgs, gains = make_inputs(name, div, images=full)
+    rig, imgs, gains = make_inputs(name, div, images=full and not args.device_images)
     seams = seam_masks_gpu(rig)
     cams = isb.cameras_from_KR(rig.Ks, rig.Rs)
     sizes = [(rig.W, rig.H)] * rig.n
@@ -432,7 +432,7 @@ def measure(name, div, args, rank, world, dev, stream, full):
 
     # ---- CPU baseline (reference CPU path, one full pass) = full-size parity vs cv2 -----------------------------------
     cpu = None
-    if rank == 0 and full and not args.no_cpu_baseline:
+    if rank == 0 and full and not args.no_cpu_baseline and imgs is not None:
         import cv2
         cv2.ipp.setUseIPP(False)  # same setting as the reference arm; bit-exact mode of the wheel
         cv2.ocl.setUseOpenCL(False)
@@ -768,6 +768,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cfg3", action="store_true", help="skip the cfg3 sub-record of the default (cfg2) line")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--device-images", action="store_true",
+                    help="generate the workload's images on the device (for rigs whose numpy generation takes minutes, e.g. cfg5 at "
+                         "full size); implies no CPU baseline and no e2e, parity is then strips vs unsharded only")
     ap.add_argument("--no-cfg1", action="store_true", help="skip the cfg1-substitute (reference default flow) sub-record")
     ap.add_argument("--inflight", type=int, default=3, help="runs in flight in the device-resident throughput loop (isb_config.pipeline_depth)")
     ap.add_argument("--video", type=int, default=0, help="also run N frames one call at a time and report p50/p95 latency")
@@ -779,6 +782,8 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.device_images:
+        args.no_cpu_baseline = args.no_e2e = True
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:
