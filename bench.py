@@ -420,11 +420,18 @@ def measure(name, div, args, rank, world, dev, stream, full):
             um = torch.zeros((ph, pw), dtype=torch.uint8, device=dev)
             c1.run(d_imgs, d_gains, d_seams, out=u8, out_mask=um)
             torch.cuda.synchronize()
-            d = (torch.from_numpy(o8).to(dev).to(torch.int16) - u8.to(torch.int16)).abs()
-            parity["vs_unsharded_same_rank"] = {"max_abs_diff_8bit": int(d.max().item()), "n_diff": int((d > 0).sum().item()),
-                                                "mask_equal": bool(torch.equal(torch.from_numpy(om).to(dev), um))}
+            dmax, ndiff, meq = 0, 0, True
+            for r0 in range(0, ph, 2048):  # row chunks: a gigapixel panorama must not be widened to int16 in one piece
+                r1 = min(ph, r0 + 2048)
+                a = torch.from_numpy(np.ascontiguousarray(o8[r0:r1])).to(dev)
+                dd = (a.to(torch.int16) - u8[r0:r1].to(torch.int16)).abs()
+                dmax = max(dmax, int(dd.max().item()))
+                ndiff += int((dd > 0).sum().item())
+                meq = meq and bool(torch.equal(torch.from_numpy(np.ascontiguousarray(om[r0:r1])).to(dev), um[r0:r1]))
+                del a, dd
+            parity["vs_unsharded_same_rank"] = {"max_abs_diff_8bit": dmax, "n_diff": ndiff, "mask_equal": meq}
             res["byte_model"] = c1.byte_model()
-            del c1, u8, um, d
+            del c1, u8, um
         else:
             res["byte_model"] = comp.byte_model()
     if world > 1:
