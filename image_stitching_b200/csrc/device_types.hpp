@@ -97,13 +97,23 @@ struct DstDev {
     int row0, row1;            // level-0 rows [row0,row1) this process owns (strip)
     int packed0;               // all tiles carry the byte-packed level 0 (fused composer)
     int max_cell_tiles;        // longest tile list of any macro cell
-    // TMA-staged cell kernel: tensor maps (CUtensorMap, device memory) of the packed level-l planes of every tile,
-    // tmap_tiles[l * n_tiles + tile] (l = 1..nb; box 24 x 18 pixels), and of the collapsed levels C[l], tmap_c[l] (viewed as
-    // uint32 pairs; box 40 x 18 words).  nullptr: the driver has no tensor-map encoder, the LDG kernels are used.
+    // TMA-fed blend kernels: tensor maps (CUtensorMap, device memory), three kinds of (nb + 1) * n_tiles maps each, indexed
+    // [kind][level][tile]: kind 0 = packed planes with 32 x 32 boxes (a block's own pixels), kind 1 = packed planes with 24 x 18
+    // boxes (the coarser level's neighbourhood), kind 2 = f32 weight planes with 32 x 32 boxes (levels >= 1); tmap_c[l] = the
+    // collapsed level C[l] viewed as uint32 pairs, 40 x 18-word boxes.  Levels whose planes are smaller than a box have no
+    // valid map and are never addressed.  nullptr: the driver has no tensor-map encoder, the LDG kernels are used.
     const void* tmap_tiles;
     const void* tmap_c;
     int n_tiles;
-    int tmap_level0;           // tmap_tiles[0 * n_tiles + tile] holds the level-0 planes too (box 32 x 32): the pipelined level-0 kernel applies
+    int tmap_level0;           // the level-0 maps of kind 0 are valid: the pipelined level-0 kernel applies
+    // pipelined kernel at levels l >= 1: covering tiles per 32 x 32 block of the level (sorted union over the macro cells under
+    // the block, feed order), CSR start + one CellTile record per entry; nullptr for levels served by the other kernels
+    // level 0 of the pipelined kernel: the cell lists without the tiles that cannot carry weight in the cell (plan-time occupancy)
+    const int* cell_start0;
+    const CellTile* cdesc0;
+    const int* blk_start[kMaxLevels];
+    const CellTile* blk_desc[kMaxLevels];
+    int blk_nbx[kMaxLevels];
 };
 
 struct OutDev {

@@ -125,6 +125,7 @@ void PyramidEngine::reset(const BlendGeometry& g, int sub_y0, int sub_h, int own
     // whatever may still read them)
     for (DevBuf* b : extra_) delete b;
     extra_.clear();
+    img_occ_.clear();
     warp_work_.clear();
     down_work_.assign(g.nb, {});
     dst_.cell_start = nullptr;
@@ -136,6 +137,15 @@ int PyramidEngine::add_tile(int img_index, int w, int h, int tlx, int tly)
     int tl[2], br[2];
     g_.tile_rect(w, h, tlx, tly, tl, br);
     return add_rect(img_index, tl[0] - g_.roi.x, tl[1] - g_.roi.y, br[0] - tl[0], br[1] - tl[1], tlx, tly, w, h);
+}
+
+void PyramidEngine::set_image_occupancy(int img, std::vector<uint8_t> grid, int cw, int ch, int gx0, int gy0)
+{
+    if (img < 0) return;
+    if ((int)img_occ_.size() <= img) img_occ_.resize(img + 1);
+    OccGrid& G = img_occ_[img];
+    G.g = std::move(grid);
+    G.cw = cw; G.ch = ch; G.x0 = gx0; G.y0 = gy0;
 }
 
 int PyramidEngine::add_rect(int img_index, int X0, int Y0, int W, int H, int tlx, int tly, int roi_w, int roi_h,
@@ -322,6 +332,17 @@ void PyramidEngine::blend(const OutDev& out, cudaStream_t st)
             for (int cy = T.y0 >> nb; cy < (T.y0 + T.h) >> nb; ++cy)
                 for (int cx = T.x0 >> nb; cx < (T.x0 + T.w) >> nb; ++cx) list[fill[cy * dst_.cells_x + cx]++] = t;
         }
+        // can tile t carry weight in panorama cell (cx, cy) [sub-panorama cell coordinates] within `dil` cells?
+        auto may_weigh = [&](int t, int cx, int cy, int dil) {
+            const TileDev& T = tiles_[t];
+            if (T.img < 0 || T.img >= (int)img_occ_.size() || img_occ_[T.img].g.empty()) return true;
+            const OccGrid& G = img_occ_[T.img];
+            const int gx = ((cx << nb) - G.x0) >> nb, gy = ((cy << nb) + sub_y0_ - G.y0) >> nb;
+            for (int y = std::max(0, gy - dil); y <= std::min(G.ch - 1, gy + dil); ++y)
+                for (int x = std::max(0, gx - dil); x <= std::min(G.cw - 1, gx + dil); ++x)
+                    if (G.g[(size_t)y * G.cw + x]) return true;
+            return false;
+        };
         size_t cbytes = 0;
         std::vector<size_t> coff(nb + 1, 0);
         for (int l = 1; l <= nb; ++l) {
@@ -356,50 +377,131 @@ void PyramidEngine::blend(const OutDev& out, cudaStream_t st)
             ISB_CUDA(cudaMemcpyAsync(dd, desc.data(), desc.size() * sizeof(CellTile), cudaMemcpyHostToDevice, st));
             ISB_CUDA(cudaStreamSynchronize(st));  // `desc` is a local
             dst_.cdesc = dd;
-            // tensor maps of the TMA-staged cell kernel: level l planes of every tile (l = 1..nb) and the collapsed levels
+            // level-0 lists without the tiles whose weights are zero in the cell for sure (no valid pixel of the image there)
+            dst_.cell_start0 = nullptr;
+            dst_.cdesc0 = nullptr;
+            {
+                std::vector<int> start0(ncell + 1, 0);
+                std::vector<CellTile> desc0;
+                for (int c = 0; c < ncell; ++c) {
+                    start0[c] = (int)desc0.size();
+                    for (int e = start[c]; e < start[c + 1]; ++e)
+                        if (may_weigh(list[e], c % dst_.cells_x, c / dst_.cells_x, 0)) desc0.push_back(desc[e]);  // level-0 record
+                }
+                start0[ncell] = (int)desc0.size();
+                int* s0 = static_cast<int*>(cells0_dev_.ensure(start0.size() * sizeof(int)));
+                CellTile* d0 = static_cast<CellTile*>(cdesc0_dev_.ensure(std::max<size_t>(desc0.size(), 1) * sizeof(CellTile)));
+                ISB_CUDA(cudaMemcpyAsync(s0, start0.data(), start0.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+                if (!desc0.empty()) ISB_CUDA(cudaMemcpyAsync(d0, desc0.data(), desc0.size() * sizeof(CellTile), cudaMemcpyHostToDevice, st));
+                ISB_CUDA(cudaStreamSynchronize(st));
+                dst_.cell_start0 = s0;
+                dst_.cdesc0 = d0;
+            }
+            // tensor maps of the TMA-fed blend kernels (see DstDev) and the per-block tile lists of the pipelined coarse levels
             dst_.tmap_tiles = dst_.tmap_c = nullptr;
+            dst_.tmap_level0 = 0;
             dst_.n_tiles = (int)tiles_.size();
+            for (int l = 0; l < kMaxLevels; ++l) {
+                dst_.blk_start[l] = nullptr;
+                dst_.blk_desc[l] = nullptr;
+                dst_.blk_nbx[l] = 0;
+            }
             if (encode_tiled_fn() && nb >= 5) {
-                const size_t nt = tiles_.size();
-                std::vector<CUtensorMap> maps((size_t)(nb + 1) * nt + (nb + 1));
+                const size_t nt = tiles_.size(), per_kind = (size_t)(nb + 1) * nt;
+                std::vector<CUtensorMap> maps(3 * per_kind + (nb + 1));
                 std::memset(maps.data(), 0, maps.size() * sizeof(CUtensorMap));
-                bool ok = true;
                 const cuuint32_t estr[2] = {1, 1};
-                bool ok0 = true;  // level-0 planes, 32 x 32 boxes (the pipelined level-0 kernel)
-                for (size_t t = 0; ok0 && t < nt; ++t) {
-                    const TileDev& T = tiles_[t];
-                    const cuuint64_t dims[2] = {(cuuint64_t)T.w, (cuuint64_t)T.h};
-                    const cuuint64_t strides[1] = {(cuuint64_t)T.ppitch[0] * sizeof(uint32_t)};
-                    const cuuint32_t box[2] = {32, 32};
-                    ok0 = T.w >= 32 && T.h >= 32 &&
-                          encode_tiled_fn()(&maps[t], CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, T.P[0], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-                }
-                dst_.tmap_level0 = ok0 ? 1 : 0;
-                for (int l = 1; ok && l <= nb; ++l) {
-                    for (size_t t = 0; ok && t < nt; ++t) {
+                auto encode = [&](CUtensorMap* m, void* base, int w, int h, size_t stride_bytes, int bw, int bh) {
+                    const cuuint64_t dims[2] = {(cuuint64_t)w, (cuuint64_t)h};
+                    const cuuint64_t strides[1] = {(cuuint64_t)stride_bytes};
+                    const cuuint32_t box[2] = {(cuuint32_t)bw, (cuuint32_t)bh};
+                    return w >= bw && h >= bh &&
+                           encode_tiled_fn()(m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+                };
+                // a level is usable by a kernel only if EVERY tile (and the collapsed plane) has a valid map of the kinds it reads
+                std::vector<char> okq(nb + 1, 1), okp(nb + 1, 1), okw(nb + 1, 1), okc(nb + 1, 1);
+                for (int l = 0; l <= nb; ++l) {
+                    for (size_t t = 0; t < nt; ++t) {
                         const TileDev& T = tiles_[t];
-                        const cuuint64_t dims[2] = {(cuuint64_t)(T.w >> l), (cuuint64_t)(T.h >> l)};
-                        const cuuint64_t strides[1] = {(cuuint64_t)T.ppitch[l] * sizeof(uint32_t)};
-                        const cuuint32_t box[2] = {24, 18};
-                        ok = encode_tiled_fn()(&maps[(size_t)l * nt + t], CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, T.P[l], dims, strides, box, estr,
-                                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+                        const int wl = T.w >> l, hl = T.h >> l;
+                        okq[l] = okq[l] && encode(&maps[(size_t)l * nt + t], T.P[l], wl, hl, (size_t)T.ppitch[l] * 4, 32, 32);
+                        okp[l] = okp[l] && l >= 1 && encode(&maps[per_kind + (size_t)l * nt + t], T.P[l], wl, hl, (size_t)T.ppitch[l] * 4, 24, 18);
+                        okw[l] = okw[l] && l >= 1 && encode(&maps[2 * per_kind + (size_t)l * nt + t], T.W[l], wl, hl, (size_t)T.wpitch[l] * 4, 32, 32);
                     }
-                    if (!ok) break;
-                    const cuuint64_t dims[2] = {(cuuint64_t)2 * (dst_.pw >> l), (cuuint64_t)(dst_.ph >> l)};
-                    const cuuint64_t strides[1] = {(cuuint64_t)dst_.cpitch[l] * sizeof(uint2)};
-                    const cuuint32_t box[2] = {40, 18};
-                    ok = encode_tiled_fn()(&maps[(size_t)(nb + 1) * nt + l], CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, dst_.C[l], dims, strides, box, estr,
-                                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+                    okc[l] = l >= 1 && encode(&maps[3 * per_kind + l], dst_.C[l], 2 * (dst_.pw >> l), dst_.ph >> l, (size_t)dst_.cpitch[l] * sizeof(uint2), 40, 18);
                 }
+                // the cell kernels read the 24 x 18 maps of level l + 1 and C[l + 1] for every level l with cells of >= 32 px
+                bool ok = true;
+                for (int l = 0; l + 5 <= nb; ++l) ok = ok && okp[l + 1] && okc[l + 1];
                 if (ok) {
                     CUtensorMap* md = static_cast<CUtensorMap*>(tmaps_blend_dev_.ensure(maps.size() * sizeof(CUtensorMap)));
                     ISB_CUDA(cudaMemcpyAsync(md, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, st));
                     ISB_CUDA(cudaStreamSynchronize(st));  // `maps` is a local
                     dst_.tmap_tiles = md;
-                    dst_.tmap_c = md + (size_t)(nb + 1) * nt;
+                    dst_.tmap_c = md + 3 * per_kind;
+                    dst_.tmap_level0 = okq[0] ? 1 : 0;
+                    // Pipelined kernel at levels 1 .. nb - 3 (cells of >= 8 px keep every box origin on a 16-byte boundary): per
+                    // 32 x 32 block of the level the sorted union of the tile lists of the macro cells under it
+                    std::vector<int> bstart;
+                    std::vector<CellTile> bdesc;
+                    std::vector<size_t> off_s(nb + 1, 0), off_d(nb + 1, 0);
+                    std::vector<char> use(nb + 1, 0);
+                    for (int l = 1; l + 3 <= nb; ++l) {
+                        if (!(okq[l] && okw[l] && okp[l + 1] && okc[l + 1])) continue;
+                        const int pwl = dst_.pw >> l, phl = dst_.ph >> l, sh = nb - l;
+                        const int nbx = (pwl + 31) / 32, nby = (phl + 31) / 32;
+                        if (nbx * nby < 296) continue;  // too few blocks to feed persistent CTAs: the quad kernel serves the level
+                        use[l] = 1;
+                        dst_.blk_nbx[l] = nbx;
+                        off_s[l] = bstart.size();
+                        off_d[l] = bdesc.size();
+                        std::vector<int> uni;
+                        int count = 0;
+                        for (int by = 0; by < nby; ++by)
+                            for (int bx = 0; bx < nbx; ++bx) {
+                                bstart.push_back(count);
+                                uni.clear();
+                                const int cx0 = (bx * 32) >> sh, cx1 = std::min(dst_.cells_x - 1, (bx * 32 + 31) >> sh);
+                                const int cy0 = (by * 32) >> sh, cy1 = std::min(dst_.cells_y - 1, (by * 32 + 31) >> sh);
+                                for (int cy = cy0; cy <= cy1; ++cy)
+                                    for (int cx = cx0; cx <= cx1; ++cx) {
+                                        const int c = cy * dst_.cells_x + cx;
+                                        uni.insert(uni.end(), list.begin() + start[c], list.begin() + start[c + 1]);
+                                    }
+                                std::sort(uni.begin(), uni.end());
+                                uni.erase(std::unique(uni.begin(), uni.end()), uni.end());
+                                for (int t : uni) {
+                                    bool any = false;  // weights of level l spread by less than one cell beyond the valid pixels
+                                    for (int cy = cy0; cy <= cy1 && !any; ++cy)
+                                        for (int cx = cx0; cx <= cx1 && !any; ++cx) any = may_weigh(t, cx, cy, 1);
+                                    if (!any) continue;
+                                    const TileDev& T = tiles_[t];
+                                    CellTile c{};
+                                    c.p0 = T.P[l]; c.p1 = T.P[l + 1]; c.w0 = T.W[l];
+                                    c.pitch0 = T.ppitch[l]; c.pitch1 = T.ppitch[l + 1];
+                                    c.ox = T.x0 >> l; c.oy = T.y0 >> l;
+                                    c.wc = T.w >> (l + 1); c.hc = T.h >> (l + 1);
+                                    c.tile = t;
+                                    bdesc.push_back(c);
+                                }
+                                count = (int)(bdesc.size() - off_d[l]);
+                            }
+                        bstart.push_back(count);
+                    }
+                    if (!bstart.empty()) {
+                        int* sd = static_cast<int*>(blk_start_dev_.ensure(bstart.size() * sizeof(int)));
+                        CellTile* dd2 = static_cast<CellTile*>(blk_desc_dev_.ensure(std::max<size_t>(bdesc.size(), 1) * sizeof(CellTile)));
+                        ISB_CUDA(cudaMemcpyAsync(sd, bstart.data(), bstart.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+                        if (!bdesc.empty())
+                            ISB_CUDA(cudaMemcpyAsync(dd2, bdesc.data(), bdesc.size() * sizeof(CellTile), cudaMemcpyHostToDevice, st));
+                        ISB_CUDA(cudaStreamSynchronize(st));
+                        for (int l = 1; l + 3 <= nb; ++l)
+                            if (use[l]) {
+                                dst_.blk_start[l] = sd + off_s[l];
+                                dst_.blk_desc[l] = dd2 + off_d[l];
+                            }
+                    }
                 }
             }
         }
@@ -1065,6 +1167,11 @@ void Composer::plan(const isb_camera* cams, const int* sizes_wh, int n, int* cor
         const int halo_top = cfg_.strip_count > 1 ? 4 * m : 0, halo_bot = cfg_.strip_count > 1 ? 3 * m : 0;
         const int sy0 = std::max(0, y0 - halo_top), sy1 = std::min(g.roi.h, (y1 + m - 1) / m * m + halo_bot);
         eng_.reset(g, sy0, std::max(sy1 - sy0, 0), y0, y1, /*packed=*/true);
+        for (int i = 0; i < n; ++i) {
+            const int cw = full[i].W >> g.nb, chh = full[i].H >> g.nb;
+            const uint8_t* o = occ.data() + occ_tiles[i].occ_off;
+            eng_.set_image_occupancy(i, std::vector<uint8_t>(o, o + (size_t)cw * chh), cw, chh, full[i].X0, full[i].Y0);
+        }
         for (const RectSpec& r : rects) {
             const int i = r.img;
             const int t = eng_.add_rect(i, r.X0, r.Y0, r.W, r.H, img_[i].roi.x, img_[i].roi.y, img_[i].roi.w, img_[i].roi.h,

@@ -112,6 +112,11 @@ public:
     const std::vector<WorkItem>& warp_work() const { return warp_work_; }
     const WorkItem* warp_work_dev() const { return warp_work_dev_.as<WorkItem>(); }
     size_t pyramid_bytes() const { return arena_.used(); }
+    // Plan-time occupancy (which macro cells of an image's full feed() tile hold a valid pixel): lets the blend skip, per cell
+    // and level, tiles whose weights are provably zero there (level 0: unoccupied cells; levels 1 .. nb-1: farther than one cell
+    // from an occupied one, because W_l spreads by 2 (2^l - 1) < 2^nb pixels).  grid: cw x ch cells whose cell (0, 0) sits at
+    // padded-panorama pixel (gx0, gy0).  Tiles without a registered grid are taken as occupied everywhere.
+    void set_image_occupancy(int img, std::vector<uint8_t> grid, int cw, int ch, int gx0, int gy0);
     bool uses_tma() const { return use_tma_; }
 
 private:
@@ -121,7 +126,7 @@ private:
     int committed_ = 0;           // tiles [0, committed_) have storage
     Arena arena_;                 // fused path: one block for all tiles
     std::vector<DevBuf*> extra_;  // classic path: one allocation per late-added tile
-    DevBuf tiles_dev_, warp_work_dev_, down_work_dev_, cells_dev_, cdesc_dev_, dst_buf_, tmaps_dev_, tmaps_blend_dev_;
+    DevBuf tiles_dev_, warp_work_dev_, down_work_dev_, cells_dev_, cdesc_dev_, dst_buf_, tmaps_dev_, tmaps_blend_dev_, blk_start_dev_, blk_desc_dev_;
     bool last_fast_ = false;
     bool use_tma_ = false;  // level 0 -> 1 pyrDown staged by TMA (packed tiles large enough for a full box)
     std::vector<WorkItem> warp_work_;
@@ -129,6 +134,9 @@ private:
     std::vector<size_t> down_off_;
     DstDev dst_{};
     bool packed_ = false;
+    struct OccGrid { std::vector<uint8_t> g; int cw = 0, ch = 0, x0 = 0, y0 = 0; };
+    std::vector<OccGrid> img_occ_;
+    DevBuf cells0_dev_, cdesc0_dev_;
 public:
     ~PyramidEngine();
 };
