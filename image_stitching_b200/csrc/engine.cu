@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <thread>
@@ -127,6 +128,7 @@ void PyramidEngine::reset(const BlendGeometry& g, int sub_y0, int sub_h, int own
     extra_.clear();
     img_occ_.clear();
     warp_work_.clear();
+    pad_work_.clear();
     down_work_.assign(g.nb, {});
     dst_.cell_start = nullptr;
     ISB_ASSERT(g.nb < kMaxLevels);
@@ -221,11 +223,39 @@ void PyramidEngine::commit_tiles(cudaStream_t st)
     last_fast_ = packed_ && first == 0;
     for (const TileDev& T : tiles_) last_fast_ = last_fast_ && (T.w >> nb) >= 2;
     warp_work_.clear();
+    pad_work_.clear();
     for (auto& v : down_work_) v.clear();
+    {   // REFLECT padding (tile pixels outside the warped ROI): mirrored by a second pass when there is enough of it to pay for
+        // the extra launch (large pyramids: the 4-cell dependency margin grows with 2^nb), else computed by kernel 1 itself
+        double tile_px = 0, roi_px = 0;
+        bool fused = end > first;
+        for (int t = first; t < end; ++t) {
+            const TileDev& T = tiles_[t];
+            fused = fused && T.img >= 0;
+            tile_px += (double)T.w * T.h;
+            const int ix = std::max(0, std::min(T.w, T.left + T.roi_w) - std::max(0, T.left));
+            const int iy = std::max(0, std::min(T.h, T.top + T.roi_h) - std::max(0, T.top));
+            roi_px += (double)ix * iy;
+        }
+        pad_fraction_ = tile_px > 0 ? 1.0 - roi_px / tile_px : 0.0;
+        mirror_pad_ = fused && pad_fraction_ > kMirrorPadThreshold;
+        if (getenv("ISB_DEBUG_PLAN"))
+            fprintf(stderr, "[isb plan] tiles %d..%d: %.1f MP, %.1f %% outside the warped ROIs -> %s\n", first, end, tile_px / 1e6,
+                    100.0 * pad_fraction_, mirror_pad_ ? "mirror_pad_kernel" : "computed by kernel 1");
+    }
     for (int t = first; t < end; ++t) {
         const TileDev& T = tiles_[t];
         for (int by = 0; by < (T.h + kWarpBlockH - 1) / kWarpBlockH; ++by)
-            for (int bx = 0; bx < (T.w + kWarpBlockW - 1) / kWarpBlockW; ++bx) warp_work_.push_back(WorkItem{t, bx, by, 0});
+            for (int bx = 0; bx < (T.w + kWarpBlockW - 1) / kWarpBlockW; ++bx) {
+                // fused path: blocks without a pixel of the warped ROI are pure REFLECT padding (mirror_pad_kernel fills them),
+                // blocks that are not entirely inside the ROI hold some
+                const int x0 = bx * kWarpBlockW - T.left, x1 = std::min((bx + 1) * kWarpBlockW, T.w) - T.left;
+                const int y0 = by * kWarpBlockH - T.top, y1 = std::min((by + 1) * kWarpBlockH, T.h) - T.top;
+                const bool touches = x1 > 0 && y1 > 0 && x0 < T.roi_w && y0 < T.roi_h;
+                const bool inside = x0 >= 0 && y0 >= 0 && x1 <= T.roi_w && y1 <= T.roi_h;
+                if (!mirror_pad_ || touches) warp_work_.push_back(WorkItem{t, bx, by, 0});
+                if (mirror_pad_ && !inside) pad_work_.push_back(WorkItem{t, bx, by, 0});
+            }
         for (int l = 0; l < nb; ++l) {
             const int ow = T.w >> (l + 1), oh = T.h >> (l + 1);
             // levels with an even output width run the register-rolling kernel (64 x 128 outputs per CTA)
@@ -270,6 +300,10 @@ void PyramidEngine::commit_tiles(cudaStream_t st)
     if (!warp_work_.empty()) {
         void* p = warp_work_dev_.ensure(warp_work_.size() * sizeof(WorkItem));
         ISB_CUDA(cudaMemcpyAsync(p, warp_work_.data(), warp_work_.size() * sizeof(WorkItem), cudaMemcpyHostToDevice, st));
+    }
+    if (!pad_work_.empty()) {
+        void* p = pad_work_dev_.ensure(pad_work_.size() * sizeof(WorkItem));
+        ISB_CUDA(cudaMemcpyAsync(p, pad_work_.data(), pad_work_.size() * sizeof(WorkItem), cudaMemcpyHostToDevice, st));
     }
     size_t total = 0;
     down_off_.assign(nb + 1, 0);
@@ -1379,7 +1413,9 @@ void Composer::run(const isb_image* imgs, const isb_gainmap* gains, const isb_ma
     }
     bool banded = false;
     for (const ImageDev& I : idev) banded = banded || I.band_lo != 0;
-    launch_warp_tiles_packed(eng_.warp_work_dev(), (int)eng_.warp_work().size(), eng_.tiles_dev(), idp, eng_.geom().nb, need_gen_, banded, st);
+    launch_warp_tiles_packed(eng_.warp_work_dev(), (int)eng_.warp_work().size(), eng_.tiles_dev(), idp, eng_.geom().nb, need_gen_, banded,
+                             eng_.mirror_pad(), st);
+    if (eng_.mirror_pad()) launch_mirror_pad(eng_.pad_work_dev(), (int)eng_.pad_work().size(), eng_.tiles_dev(), st);
     // ---- stage 2: pyramids (kernel 2) ---------------------------------------------------------
     ISB_CUDA(cudaEventRecord(ev_[2], st));
     eng_.build_pyramids(0, (int)eng_.tiles().size(), st);

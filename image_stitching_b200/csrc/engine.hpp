@@ -111,6 +111,10 @@ public:
     int own_y1() const { return own_y1_; }
     const std::vector<WorkItem>& warp_work() const { return warp_work_; }
     const WorkItem* warp_work_dev() const { return warp_work_dev_.as<WorkItem>(); }
+    bool mirror_pad() const { return mirror_pad_; }
+    double pad_fraction() const { return pad_fraction_; }
+    const std::vector<WorkItem>& pad_work() const { return pad_work_; }
+    const WorkItem* pad_work_dev() const { return pad_work_dev_.as<WorkItem>(); }
     size_t pyramid_bytes() const { return arena_.used(); }
     // Plan-time occupancy (which macro cells of an image's full feed() tile hold a valid pixel): lets the blend skip, per cell
     // and level, tiles whose weights are provably zero there (level 0: unoccupied cells; levels 1 .. nb-1: farther than one cell
@@ -129,7 +133,11 @@ private:
     DevBuf tiles_dev_, warp_work_dev_, down_work_dev_, cells_dev_, cdesc_dev_, dst_buf_, tmaps_dev_, tmaps_blend_dev_, blk_start_dev_, blk_desc_dev_;
     bool last_fast_ = false;
     bool use_tma_ = false;  // level 0 -> 1 pyrDown staged by TMA (packed tiles large enough for a full box)
-    std::vector<WorkItem> warp_work_;
+    std::vector<WorkItem> warp_work_, pad_work_;  // blocks kernel 1 computes / blocks that hold REFLECT padding (kernel 1b)
+    DevBuf pad_work_dev_;
+    bool mirror_pad_ = false;
+    double pad_fraction_ = 0.0;
+    static constexpr double kMirrorPadThreshold = 0.12;  // share of the tile area outside the warped ROIs
     std::vector<std::vector<WorkItem>> down_work_;  // per level, for tiles of the last commit
     std::vector<size_t> down_off_;
     DstDev dst_{};

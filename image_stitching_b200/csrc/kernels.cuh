@@ -93,9 +93,13 @@ struct OccTile { int img; int left, top; int w, h; long long occ_off; };
 void launch_occupancy(const OccTile* tiles_dev, int n_tiles, int max_w, int max_h, const ImageDev* imgs, int nb,
                       uint8_t* occ, cudaStream_t st);
 // fused warp -> packed level 0
-// banded_sources: some ImageDev::band_lo is non-zero (see ImageDev)
+// banded_sources: some ImageDev::band_lo is non-zero (see ImageDev); mirrored_padding: `work` omits the blocks outside the warped
+// ROIs and launch_mirror_pad follows (the kernel then skips every pixel outside the ROI)
 void launch_warp_tiles_packed(const WorkItem* work, int n_work, const TileDev* tiles, const ImageDev* imgs, int nb, uint32_t gen,
-                              bool banded_sources, cudaStream_t st);
+                              bool banded_sources, bool mirrored_padding, cudaStream_t st);
+// kernel 1b: mirrors the tile pixels outside the warped ROI (REFLECT padding of feed()) from the pixels kernel 1 stored; `work`
+// lists the kWarpBlockW x kWarpBlockH blocks that hold padding
+void launch_mirror_pad(const WorkItem* work, int n_work, const TileDev* tiles, cudaStream_t st);
 // per-run seam preparation in one launch: (1) cv::dilate(3x3) of every image's seam mask, imgs[i].seam_raw -> imgs[i].seam;
 // (2) seam-aware culling: every macro cell that holds a valid pixel (plan-time occupancy) and in which the upsampled
 // dilated seam mask can be non-zero stamps `gen` into need[] for all cells within 4 cells of it.  One OccTile per image
