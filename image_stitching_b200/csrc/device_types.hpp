@@ -50,6 +50,10 @@ struct TileDev {
     // the output and the warp kernel zero-fills them instead of computing them.  Stamped on the device every run.
     const uint32_t* need;
     int need_cw;
+    // REFLECT padding (tile pixels outside the warped ROI) of this tile is mirrored from computed pixels by mirror_pad_kernel:
+    // set when every padding pixel's mirror image lies inside the tile (a tile cut by a strip or by support culling may lack
+    // the rows / columns its padding reflects onto; kernel 1 then computes the padding itself)
+    int mirror;
     // Fused path (`packed` != 0): the warped image is 8-bit, so every Gaussian level stays in [0,255] and is stored
     // byte-packed, one uint32 per pixel = b | g<<8 | r<<16 (| m<<24 at level 0, m = the 8-bit blend mask, whose
     // weight is m * (1/255) exactly as feed() forms it).  Level 0 therefore costs 4 B/px instead of 10 B/px and one

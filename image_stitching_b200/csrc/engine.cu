@@ -239,6 +239,30 @@ void PyramidEngine::commit_tiles(cudaStream_t st)
         }
         pad_fraction_ = tile_px > 0 ? 1.0 - roi_px / tile_px : 0.0;
         mirror_pad_ = fused && pad_fraction_ > kMirrorPadThreshold;
+        // per tile: mirrored only if every padding column / row reflects onto a column / row the tile holds
+        auto refl = [](int p, int n) {  // cv::BORDER_REFLECT index (device_math.cuh: reflect)
+            if (n == 1) return 0;
+            if (p < 0) p = -p - 1;
+            p %= 2 * n;
+            return p < n ? p : 2 * n - 1 - p;
+        };
+        for (int t = first; t < end; ++t) {
+            TileDev& T = tiles_[t];
+            bool ok = mirror_pad_;
+            for (int x = 0; ok && x < T.w; ++x) {
+                const int rx0 = x - T.left;
+                if (rx0 >= 0 && rx0 < T.roi_w) { x = std::max(x, std::min(T.w, T.left + T.roi_w) - 1); continue; }
+                const int sx = refl(rx0, T.roi_w) + T.left;
+                ok = sx >= 0 && sx < T.w;
+            }
+            for (int y = 0; ok && y < T.h; ++y) {
+                const int ry0 = y - T.top;
+                if (ry0 >= 0 && ry0 < T.roi_h) { y = std::max(y, std::min(T.h, T.top + T.roi_h) - 1); continue; }
+                const int sy = refl(ry0, T.roi_h) + T.top;
+                ok = sy >= 0 && sy < T.h;
+            }
+            T.mirror = ok ? 1 : 0;
+        }
         if (getenv("ISB_DEBUG_PLAN"))
             fprintf(stderr, "[isb plan] tiles %d..%d: %.1f MP, %.1f %% outside the warped ROIs -> %s\n", first, end, tile_px / 1e6,
                     100.0 * pad_fraction_, mirror_pad_ ? "mirror_pad_kernel" : "computed by kernel 1");
@@ -253,8 +277,8 @@ void PyramidEngine::commit_tiles(cudaStream_t st)
                 const int y0 = by * kWarpBlockH - T.top, y1 = std::min((by + 1) * kWarpBlockH, T.h) - T.top;
                 const bool touches = x1 > 0 && y1 > 0 && x0 < T.roi_w && y0 < T.roi_h;
                 const bool inside = x0 >= 0 && y0 >= 0 && x1 <= T.roi_w && y1 <= T.roi_h;
-                if (!mirror_pad_ || touches) warp_work_.push_back(WorkItem{t, bx, by, 0});
-                if (mirror_pad_ && !inside) pad_work_.push_back(WorkItem{t, bx, by, 0});
+                if (!T.mirror || touches) warp_work_.push_back(WorkItem{t, bx, by, 0});
+                if (T.mirror && !inside) pad_work_.push_back(WorkItem{t, bx, by, 0});
             }
         for (int l = 0; l < nb; ++l) {
             const int ow = T.w >> (l + 1), oh = T.h >> (l + 1);
