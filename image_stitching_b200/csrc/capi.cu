@@ -63,6 +63,7 @@ int isb_set_stream(void* s)
     set_current_stream(static_cast<cudaStream_t>(s));
     return ISB_OK;
 }
+void isb_reload_env(void) { reload_env_switches(); }
 long long isb_launch_count(int reset) { return launch_count(reset != 0); }
 
 // ---- cameras / pose math ------------------------------------------------------------------------

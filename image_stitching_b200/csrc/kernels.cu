@@ -40,11 +40,25 @@ cudaError_t take_launch_error()
     return e;
 }
 
-bool pdl_enabled()
+// Measurement switches (all default to the production setting) are read from the environment ONCE; tools that flip them
+// inside one process (tools/ab_env.py) call isb_reload_env() afterwards.
+static EnvSwitches read_env_switches()
 {
-    const char* e = getenv("ISB_PDL");  // read on every launch: a tuning switch, a few ns next to a launch
-    return !(e && e[0] == '0');
+    auto off = [](const char* name) {
+        const char* e = getenv(name);
+        return e && e[0] == '0';
+    };
+    EnvSwitches s;
+    s.pdl = !off("ISB_PDL");
+    s.blend_tma = !off("ISB_BLEND_TMA");
+    s.blend_pipe = !off("ISB_BLEND_PIPE");
+    s.staged_stores = getenv("ISB_STAGED_STORES") != nullptr;
+    return s;
 }
+static EnvSwitches g_env = read_env_switches();
+const EnvSwitches& env_switches() { return g_env; }
+void reload_env_switches() { g_env = read_env_switches(); }
+bool pdl_enabled() { return g_env.pdl; }
 
 // ------------------------------------------------------------------------------------------------
 // classic API kernels

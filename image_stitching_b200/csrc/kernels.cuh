@@ -16,6 +16,15 @@ void count_launch();
 // trigger only fires once ALL CTAs of this grid have executed it) and then waits until the grid it depends on has
 // completed and flushed its memory.  Launched without the attribute (classic per-call API) both instructions are no-ops.
 bool pdl_enabled();  // ISB_PDL=0 turns the launch attribute off (A/B measurements)
+// run-time measurement switches, read from the environment once per process (reload_env_switches() re-reads them)
+struct EnvSwitches {
+    bool pdl;            // ISB_PDL=0: launch the chain without programmatic stream serialization
+    bool blend_tma;      // ISB_BLEND_TMA=0: LDG cell kernels instead of the TMA-staged ones
+    bool blend_pipe;     // ISB_BLEND_PIPE=0: no pipelined (persistent) blend kernels
+    bool staged_stores;  // ISB_STAGED_STORES: force the staged 16-byte store path of the level-0 blend on local memory
+};
+const EnvSwitches& env_switches();
+void reload_env_switches();
 // first error a chained launch returned since the last call (cudaSuccess if none); the engine turns it into ISB_ERR_GPU_API
 void note_launch_error(cudaError_t e);
 cudaError_t take_launch_error();

@@ -65,6 +65,9 @@ ISB_API const char* isb_version(void);
 ISB_API int isb_device_count(void);
 /* stream all subsequent work of the calling thread's handles is enqueued on (cudaStream_t; NULL = default stream) */
 ISB_API int isb_set_stream(void* cuda_stream);
+/* the measurement switches (ISB_PDL, ISB_BLEND_PIPE, ISB_BLEND_TMA, ISB_STAGED_STORES) are read from the
+ * environment once per process; a tool that changes them afterwards calls this to have them re-read */
+ISB_API void isb_reload_env(void);
 /* counts kernel launches made by this library since the last reset (bench.py's `gpu_launches`) */
 ISB_API long long isb_launch_count(int reset);
 

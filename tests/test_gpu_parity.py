@@ -429,6 +429,7 @@ def test_compose_8bit_device_output_paths(pad, staged, monkeypatch):
     torch = pytest.importorskip("torch")
     if staged:
         monkeypatch.setenv("ISB_STAGED_STORES", "1")
+    isb.lib().isb_reload_env()  # the switches are read once per process
     rig, imgs, gains, nb = make_case("cfg2", 8, 5)
     seams = seam_masks_oracle(rig)
     ref = isb.compose(imgs, rig.Ks, rig.Rs, rig.scale, rig.warp, nb, gains, seams)  # generic stores (16SC3 requested)
@@ -442,6 +443,8 @@ def test_compose_8bit_device_output_paths(pad, staged, monkeypatch):
     c.run([torch.from_numpy(im).cuda() for im in imgs], gains, seams, out=o8, out_mask=om, out_pitch=p8, mask_pitch=pm)
     torch.cuda.synchronize()
     o8, om = o8.cpu().numpy(), om.cpu().numpy()
+    monkeypatch.undo()
+    isb.lib().isb_reload_env()  # back to the production switches for the tests that follow
     assert np.array_equal(o8[:, :w * 3].reshape(h, w, 3), ref["result8"]) and np.array_equal(om[:, :w], ref["mask"])
     assert (o8[:, w * 3:] == 7).all() and (om[:, w:] == 7).all()  # nothing written beyond the panorama's columns
 

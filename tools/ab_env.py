@@ -38,6 +38,7 @@ def main():
     for variant in a.variants.split(";"):
         env = dict(kv.split("=", 1) for kv in variant.split())
         os.environ.update(env)
+        isb.lib().isb_reload_env()
         comp = isb.Composer(rig.warp, rig.scale, rig.nb)
         _, _, roi = comp.plan(cams, [(rig.W, rig.H)] * rig.n)
         pw, ph = roi[2], roi[3]
@@ -68,6 +69,7 @@ def main():
         print(f"{variant}: {best:.4f} ms/step equal={same} stages={ {k: round(v, 3) for k, v in stages.items()} }", flush=True)
         for k in env:
             os.environ.pop(k, None)
+        isb.lib().isb_reload_env()
         del comp
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
     json.dump(rows, open(a.out, "w"), indent=1)
