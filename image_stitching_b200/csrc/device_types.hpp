@@ -125,6 +125,7 @@ struct OutDev {
     uint8_t* mask; long long mpitch;     // 8UC1, may be null
     int16_t* out16; long long pitch16;   // 16SC3 interleaved (bytes pitch), may be null
     int fast8;                           // set by the launcher: the packed 8-bit store path applies
+    int odd;                             // set by the launcher: some pointer or pitch of out8 / mask is odd (rows may start at odd addresses)
     int staged;                          // set by the launcher: strip-sharded output, staged vector stores (any alignment)
     int peer;                            // set by the composer: strip-sharded run, the output may live on another GPU
 };

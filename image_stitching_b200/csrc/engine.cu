@@ -1294,21 +1294,25 @@ void Composer::run(const isb_image* imgs, const isb_gainmap* gains, const isb_ma
     dyn_.begin();
     h2d_bytes_ = 0;
     std::vector<size_t> src_off(n, 0), gain_off(n, 0), sraw_off(n, 0), sdil_off(n, 0);
+    std::vector<char> src_dev(n, 0), gain_dev(n, 0), seam_dev(n, 0);  // one pointer-attribute query per buffer and run
     for (int i = 0; i < n; ++i) {
         if (tiles_of_image_[i].empty()) continue;
         const isb_image& im = imgs[i];
         if (!im.data) throw Error(ISB_ERR_NULL_PTR, "image data is null");
         ISB_ASSERT(im.width == img_[i].src_w && im.height == img_[i].src_h && im.pitch >= (size_t)im.width * 3);
-        if (mem_kind(im.data) != MemKind::Device)  // rows [band lo, band hi] only, + one row: room for the sampler's 16-byte
+        src_dev[i] = mem_kind(im.data) == MemKind::Device;
+        if (!src_dev[i])  // rows [band lo, band hi] only, + one row: room for the sampler's 16-byte
             src_off[i] = dyn_.take((size_t)im.width * 3 * (src_band_[2 * i + 1] - src_band_[2 * i] + 2) + 32);  // windows and its speculative loads
         if (gains && gains[i].data) {
             ISB_ASSERT(gains[i].width > 0 && gains[i].height > 0);
-            if (mem_kind(gains[i].data) != MemKind::Device)
+            gain_dev[i] = mem_kind(gains[i].data) == MemKind::Device;
+            if (!gain_dev[i])
                 gain_off[i] = dyn_.take((size_t)gains[i].width * gains[i].height * sizeof(float));
         }
         if (seams && seams[i].data) {
             ISB_ASSERT(seams[i].width > 0 && seams[i].height > 0 && seams[i].pitch >= (size_t)seams[i].width);
-            if (mem_kind(seams[i].data) != MemKind::Device) sraw_off[i] = dyn_.take((size_t)seams[i].width * seams[i].height);
+            seam_dev[i] = mem_kind(seams[i].data) == MemKind::Device;
+            if (!seam_dev[i]) sraw_off[i] = dyn_.take((size_t)seams[i].width * seams[i].height);
             sdil_off[i] = dyn_.take((size_t)seams[i].width * seams[i].height);
         }
     }
@@ -1343,7 +1347,7 @@ void Composer::run(const isb_image* imgs, const isb_gainmap* gains, const isb_ma
             const double bound = 3.0 * (double)kmax * std::max(1.0, (double)P.row_bmax);
             I.zlo = (finite && bound < 0x1p40) ? 0x1p-40f : INFINITY;
         }
-        if (mem_kind(im.data) == MemKind::Device) {
+        if (src_dev[i]) {
             I.src = im.data;
             I.spitch = (long long)im.pitch;
         } else {
@@ -1363,11 +1367,11 @@ void Composer::run(const isb_image* imgs, const isb_gainmap* gains, const isb_ma
             const long long room = (long long)I.sbytes - 16 - 3ll * (I.sw - 2);
             I.fast_h = (I.sbytes && I.sw >= 2 && room >= I.spitch) ? (int)std::min<long long>(room / I.spitch, I.sh - 1) : 0;
             // staged host sources end in a spare row: every tap row of the band may use the vectorised sampler
-            if (I.sbytes && I.sw >= 2 && mem_kind(im.data) != MemKind::Device) I.fast_h = I.sh - 1;
+            if (I.sbytes && I.sw >= 2 && !src_dev[i]) I.fast_h = I.sh - 1;
         }
         if (gains && gains[i].data) {
             const isb_gainmap& g = gains[i];
-            const bool gdev = mem_kind(g.data) == MemKind::Device;  // device-resident gain maps are used in place
+            const bool gdev = gain_dev[i];  // device-resident gain maps are used in place
             if (!gdev) ISB_CUDA(cudaMemcpyAsync(db + gain_off[i], g.data, (size_t)g.width * g.height * sizeof(float), cudaMemcpyDefault, st));
             if (P.gain_w != g.width || P.gain_h != g.height) {  // coefficient tables depend on the sizes only
                 build_linear_f32_table(g.width, P.roi.w, true, gx);
@@ -1384,7 +1388,7 @@ void Composer::run(const isb_image* imgs, const isb_gainmap* gains, const isb_ma
         }
         if (seams && seams[i].data) {
             const isb_mask& m = seams[i];
-            if (mem_kind(m.data) == MemKind::Device) {
+            if (seam_dev[i]) {
                 I.seam_raw = m.data;
                 I.seam_raw_pitch = (int)m.pitch;
             } else {
@@ -1530,7 +1534,7 @@ void Composer::run(const isb_image* imgs, const isb_gainmap* gains, const isb_ma
     // host-visible results (or host-owned inputs) => the call is synchronous; all-device calls stay stream-ordered
     bool any_host = (out->data && !d8) || (out->mask && !dm) || (out->data16 && !d16);
     for (int i = 0; i < n && !any_host; ++i)
-        if (!tiles_of_image_[i].empty() && mem_kind(imgs[i].data) == MemKind::Host) any_host = true;
+        if (!tiles_of_image_[i].empty() && !src_dev[i] && mem_kind(imgs[i].data) == MemKind::Host) any_host = true;
     if (any_host && !cfg_.async_mode) ISB_CUDA(cudaStreamSynchronize(st));
 }
 

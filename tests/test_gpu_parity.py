@@ -449,6 +449,33 @@ def test_compose_8bit_device_output_paths(pad, staged, monkeypatch):
     assert (o8[:, w * 3:] == 7).all() and (om[:, w:] == 7).all()  # nothing written beyond the panorama's columns
 
 
+@pytest.mark.parametrize("base_off,pad", [(1, 0), (1, 1), (0, 3), (3, 5)])
+def test_compose_8bit_odd_addresses_fast_path(base_off, pad):
+    """A tightly packed panorama of odd width (cfg3: 46655 columns) has rows at odd addresses.  The pipelined level-0 blend
+    serves it too (rows at odd addresses split the first and last colour byte off their 16-bit stores): odd base pointer with
+    an even pitch (every row odd), odd base with an odd pitch, even base with an odd pitch (rows alternate)."""
+    torch = pytest.importorskip("torch")
+    rig, imgs, gains, nb = make_case("cfg2", 8, 5)
+    seams = seam_masks_oracle(rig)
+    ref = orc.compose(imgs, rig.Ks, rig.Rs, rig.scale, rig.warp, nb, gains, seams)
+    c = isb.Composer(rig.warp, rig.scale, nb)
+    c.plan(isb.cameras_from_KR(rig.Ks, rig.Rs), [(rig.W, rig.H)] * rig.n)
+    x, y, w, h = c.dst_roi
+    p8, pm = w * 3 + pad, w + pad
+    b8 = torch.full((h * p8 + 64,), 7, dtype=torch.uint8, device="cuda")
+    bm = torch.full((h * pm + 64,), 7, dtype=torch.uint8, device="cuda")
+    o8, om = b8[base_off:], bm[base_off:]
+    assert o8.data_ptr() % 2 == base_off % 2
+    c.run([torch.from_numpy(im).cuda() for im in imgs], gains, seams, out=o8, out_mask=om, out_pitch=p8, mask_pitch=pm)
+    torch.cuda.synchronize()
+    b8, bm = b8.cpu().numpy(), bm.cpu().numpy()
+    g8 = b8[base_off:base_off + h * p8].reshape(h, p8)
+    gm = bm[base_off:base_off + h * pm].reshape(h, pm)
+    assert np.array_equal(g8[:, :w * 3].reshape(h, w, 3), ref["result8"]) and np.array_equal(gm[:, :w], ref["mask"])
+    assert (g8[:, w * 3:] == 7).all() and (gm[:, w:] == 7).all() and (b8[:base_off] == 7).all() and (bm[:base_off] == 7).all()
+    assert (b8[base_off + h * p8:] == 7).all() and (bm[base_off + h * pm:] == 7).all()  # nothing written outside the rows
+
+
 @pytest.mark.parametrize("tag", ["feather", "no"])
 def test_loop_with_simple_blenders(tag):
     """The compositing loop call by call through the C ABI with blend_type feather / no (image_stitching.cpp:1175-1191):
