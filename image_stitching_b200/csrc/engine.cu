@@ -289,29 +289,41 @@ void PyramidEngine::commit_tiles(cudaStream_t st)
                 for (int bx = 0; bx < (ow + bw - 1) / bw; ++bx) down_work_[l].push_back(WorkItem{t, bx, by, 0});
         }
     }
-    // level 0 -> 1 of the fused path goes through TMA-staged tiles when every tile can hold a full box
+    // pyrDown of the fused path goes through TMA-staged tiles at every level l <= nb - 2 (even output widths) at which every tile
+    // can hold a full box: level 0 stages the packed pixels (their mask byte is the weight), levels >= 1 the pixels and the f32
+    // weight plane.  Maps live at [(2 l + kind) * n_tiles + tile], kind 0 = pixels, 1 = weights.
     use_tma_ = false;
+    tma_levels_ = 0;
     if (packed_ && first == 0 && nb >= 2 && encode_tiled_fn()) {
-        bool ok = true;
-        for (const TileDev& T : tiles_) ok = ok && T.w >= kTmaBoxW && T.h >= kTmaBoxH;
-        std::vector<CUtensorMap> maps(tiles_.size());
-        for (size_t t = 0; ok && t < tiles_.size(); ++t) {
-            const TileDev& T = tiles_[t];
-            const cuuint64_t dims[2] = {(cuuint64_t)T.w, (cuuint64_t)T.h};
-            const cuuint64_t strides[1] = {(cuuint64_t)T.ppitch[0] * sizeof(uint32_t)};
+        const size_t nt = tiles_.size();
+        std::vector<CUtensorMap> maps(2 * (size_t)nb * nt);
+        std::memset(maps.data(), 0, maps.size() * sizeof(CUtensorMap));
+        auto encode = [&](CUtensorMap* m, void* base, int w, int h, size_t stride_bytes) {
+            const cuuint64_t dims[2] = {(cuuint64_t)w, (cuuint64_t)h};
+            const cuuint64_t strides[1] = {(cuuint64_t)stride_bytes};
             const cuuint32_t box[2] = {(cuuint32_t)kTmaBoxW, (cuuint32_t)kTmaBoxH};
             const cuuint32_t estr[2] = {1, 1};
-            ok = encode_tiled_fn()(&maps[t], CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, T.P[0], dims, strides, box, estr,
-                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-        }
-        if (ok) {
-            down_work_[0].clear();
-            for (int t = 0; t < (int)tiles_.size(); ++t) {
-                const int ow = tiles_[t].w >> 1, oh = tiles_[t].h >> 1;
-                for (int by = 0; by < (oh + kTmaOutH - 1) / kTmaOutH; ++by)
-                    for (int bx = 0; bx < (ow + kTmaOutW - 1) / kTmaOutW; ++bx) down_work_[0].push_back(WorkItem{t, bx, by, 0});
+            return encode_tiled_fn()(m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+        };
+        for (int l = 0; l + 2 <= nb && l < env_switches().pyrdown_tma_levels; ++l) {  // consecutive levels from 0: the first one that does not qualify ends the list
+            bool ok = true;
+            for (size_t t = 0; ok && t < nt; ++t) {
+                const TileDev& T = tiles_[t];
+                const int wl = T.w >> l, hl = T.h >> l;
+                ok = wl >= kTmaBoxW && hl >= kTmaBoxH && encode(&maps[(2 * (size_t)l) * nt + t], T.P[l], wl, hl, (size_t)T.ppitch[l] * sizeof(uint32_t));
+                if (ok && l >= 1) ok = encode(&maps[(2 * (size_t)l + 1) * nt + t], T.W[l], wl, hl, (size_t)T.wpitch[l] * sizeof(float));
             }
+            if (!ok) break;
+            tma_levels_ = l + 1;
+            down_work_[l].clear();
+            for (int t = 0; t < (int)nt; ++t) {
+                const int ow = tiles_[t].w >> (l + 1), oh = tiles_[t].h >> (l + 1);
+                for (int by = 0; by < (oh + kTmaOutH - 1) / kTmaOutH; ++by)
+                    for (int bx = 0; bx < (ow + kTmaOutW - 1) / kTmaOutW; ++bx) down_work_[l].push_back(WorkItem{t, bx, by, 0});
+            }
+        }
+        if (tma_levels_ > 0) {
             void* md = tmaps_dev_.ensure(maps.size() * sizeof(CUtensorMap));
             ISB_CUDA(cudaMemcpyAsync(md, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, st));
             ISB_CUDA(cudaStreamSynchronize(st));  // `maps` is a local
@@ -354,7 +366,10 @@ void PyramidEngine::build_pyramids(int first, int end, cudaStream_t st)
     const WorkItem* base = down_work_dev_.as<WorkItem>();
     for (int l = 0; l < g_.nb; ++l) {
         const int n = (int)(down_off_[l + 1] - down_off_[l]);
-        if (l == 0 && use_tma_) launch_pyrdown_tma(base + down_off_[l], n, tiles_dev(), tmaps_dev_.as<void>(), st);
+        if (l < tma_levels_) {
+            const CUtensorMap* m = tmaps_dev_.as<CUtensorMap>() + (2 * (size_t)l) * tiles_.size();
+            launch_pyrdown_tma(base + down_off_[l], n, tiles_dev(), m, m + tiles_.size(), l, st);
+        }
         else if (fast_down(l)) launch_pyrdown_fast(base + down_off_[l], n, tiles_dev(), l, packed_, fast_rows(l), l + 1 == g_.nb, st);
         else launch_pyrdown_tiles(base + down_off_[l], n, tiles_dev(), l, st);
     }

@@ -132,7 +132,8 @@ private:
     std::vector<DevBuf*> extra_;  // classic path: one allocation per late-added tile
     DevBuf tiles_dev_, warp_work_dev_, down_work_dev_, cells_dev_, cdesc_dev_, dst_buf_, tmaps_dev_, tmaps_blend_dev_, blk_start_dev_, blk_desc_dev_;
     bool last_fast_ = false;
-    bool use_tma_ = false;  // level 0 -> 1 pyrDown staged by TMA (packed tiles large enough for a full box)
+    bool use_tma_ = false;  // pyrDown staged by TMA at levels [0, tma_levels_) (packed tiles large enough for a full box there)
+    int tma_levels_ = 0;
     std::vector<WorkItem> warp_work_, pad_work_;  // blocks kernel 1 computes / blocks that hold REFLECT padding (kernel 1b)
     DevBuf pad_work_dev_;
     bool mirror_pad_ = false;

@@ -53,6 +53,8 @@ static EnvSwitches read_env_switches()
     s.blend_tma = !off("ISB_BLEND_TMA");
     s.blend_pipe = !off("ISB_BLEND_PIPE");
     s.staged_stores = getenv("ISB_STAGED_STORES") != nullptr;
+    const char* lv = getenv("ISB_PYRDOWN_TMA_LEVELS");
+    s.pyrdown_tma_levels = (lv && lv[0] >= '0' && lv[0] <= '9') ? atoi(lv) : 64;
     return s;
 }
 static EnvSwitches g_env = read_env_switches();

@@ -22,6 +22,7 @@ struct EnvSwitches {
     bool blend_tma;      // ISB_BLEND_TMA=0: LDG cell kernels instead of the TMA-staged ones
     bool blend_pipe;     // ISB_BLEND_PIPE=0: no pipelined (persistent) blend kernels
     bool staged_stores;  // ISB_STAGED_STORES: force the staged 16-byte store path of the level-0 blend on local memory
+    int pyrdown_tma_levels;  // ISB_PYRDOWN_TMA_LEVELS=n: TMA-staged pyrDown at the first n levels only (0: none; default: all that qualify)
 };
 const EnvSwitches& env_switches();
 void reload_env_switches();
@@ -121,8 +122,9 @@ void launch_seam_prep(const ImageDev* imgs_dev, int n_img, const int* blk_dev, i
 // odd_width: the level's output width may be odd (last level of packed tiles at least two macro cells wide)
 void launch_pyrdown_fast(const WorkItem* work, int n_work, const TileDev* tiles, int level, bool packed, int rows_per_warp,
                          bool odd_width, cudaStream_t st);
-// TMA-staged level 0 -> 1 pyrDown of packed tiles: `tmaps` = one CUtensorMap per tile (level-0 plane), device memory
-void launch_pyrdown_tma(const WorkItem* work, int n_work, const TileDev* tiles, const void* tmaps, cudaStream_t st);
+// TMA-staged pyrDown of packed tiles, level -> level + 1: pmaps / wmaps = one CUtensorMap per tile over the level's packed pixels /
+// f32 weights (device memory; wmaps is not read at level 0, whose weights are the mask bytes of the pixels)
+void launch_pyrdown_tma(const WorkItem* work, int n_work, const TileDev* tiles, const void* pmaps, const void* wmaps, int level, cudaStream_t st);
 constexpr int kTmaOutW = 64, kTmaOutH = 32;                          // outputs per CTA
 constexpr int kTmaBoxW = 2 * kTmaOutW + 8, kTmaBoxH = 2 * kTmaOutH + 3;  // 136 x 67 input box (x origin 2*ox0 - 4)
 // 2x2-quad accumulate + normalise + collapse for level < nb
