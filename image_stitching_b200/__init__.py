@@ -710,6 +710,34 @@ def crop(image):
     return out[y:y + h, x:x + w], (x, y, w, h)
 
 
+def imencode_jpg(image, quality=95):
+    """cv2.imencode('.jpg', image) / the file cv::imwrite("result.jpg", result) writes (image_stitching.cpp:1228): bytes.
+    image: HxWx3 uint8 or int16 (numpy, BGR), or a torch.cuda uint8 / int16 tensor."""
+    if hasattr(image, "data_ptr"):
+        assert image.is_contiguous() and image.dim() == 3 and image.shape[2] == 3
+        h, w = int(image.shape[0]), int(image.shape[1])
+        is16 = int(image.element_size() == 2)
+        ptr, pitch = C.c_void_p(image.data_ptr()), w * 3 * image.element_size()
+        keep = image
+    else:
+        keep = np.ascontiguousarray(image)
+        assert keep.ndim == 3 and keep.shape[2] == 3 and keep.dtype in (np.uint8, np.int16)
+        h, w = keep.shape[:2]
+        is16 = int(keep.dtype == np.int16)
+        ptr, pitch = keep.ctypes.data_as(C.c_void_p), keep.strides[0]
+    cap = 1024 + w * h * 3 // 2  # room for ordinary images; the call reports the size it needs when this is too small
+    n = C.c_size_t(0)
+    for _ in range(2):
+        buf = np.empty(cap, np.uint8)
+        rc = lib().isb_jpeg_encode(ptr, w, h, C.c_size_t(pitch), is16, int(quality), buf.ctypes.data_as(C.c_void_p), C.c_size_t(cap), C.byref(n))
+        if rc == 0:
+            return buf[:n.value].tobytes()
+        if n.value <= cap:
+            _chk(rc)
+        cap = int(n.value)
+    _chk(rc)
+
+
 def cameras_from_KR(Ks, Rs):
     """isb_camera list from float32 K = [[f,0,cx],[0,f*a,cy],[0,0,1]] and R."""
     cams = []

@@ -15,7 +15,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libisb.so")
-SOURCES = ["kernels.cu", "kernels_fast.cu", "simple_blend.cu", "crop.cu", "engine.cu", "capi.cu", "geometry.cpp", "cam_io.cpp"]
+SOURCES = ["kernels.cu", "kernels_fast.cu", "simple_blend.cu", "crop.cu", "jpeg.cu", "engine.cu", "capi.cu", "geometry.cpp", "cam_io.cpp"]
 HEADERS = ["kernels.cuh", "device_math.cuh", "glibc_math.cuh", "engine.hpp", "device_types.hpp", "geometry.hpp", "cam_io.hpp", "pose_math.hpp",
            os.path.join("..", "..", "include", "image_stitching.h")]
 

@@ -438,6 +438,12 @@ int isb_crop_rect_image(const void* img, int w, int h, size_t pitch, int is_16s,
     return guarded([&] { crop_rect_image(img, w, h, pitch, is_16s, rect, n_points); });
 }
 
+// ---- imwrite(.jpg) ------------------------------------------------------------------------------------
+int isb_jpeg_encode(const void* image, int w, int h, size_t pitch, int is_16s, int quality, uint8_t* out, size_t capacity, size_t* out_size)
+{
+    return guarded([&] { jpeg_encode(image, w, h, pitch, is_16s, quality, out, capacity, out_size); });
+}
+
 // ---- composer ---------------------------------------------------------------------------------------
 isb_composer* isb_composer_create(const isb_config* cfg)
 {

@@ -194,6 +194,9 @@ void resize_linear_exact(const uint8_t* src, int sw, int sh, int ch, size_t spit
 void crop_rect(const uint8_t* mask, int W, int H, size_t pitch, int rect_xywh[4], int* n_points);
 void crop_rect_image(const void* img, int W, int H, size_t pitch, int is_16s, int rect_xywh[4], int* n_points);
 
+// cv::imwrite("result.jpg", result) of the reference (image_stitching.cpp:1228) on the device: jpeg.cu
+void jpeg_encode(const void* image, int W, int H, size_t pitch, int is_16s, int quality, uint8_t* out, size_t capacity, size_t* out_size);
+
 void seam_mask_apply(const uint8_t* seam, int mw, int mh, size_t spitch, uint8_t* mask, int w, int h, size_t pitch);
 
 class Blender {

@@ -353,6 +353,19 @@ ISB_API int isb_crop_rect(const uint8_t* mask, int width, int height, size_t pit
 ISB_API int isb_crop_rect_image(const void* image, int width, int height, size_t pitch_bytes, int is_16s, int rect_xywh[4],
                                 int* n_contour_points);
 
+/* ==============================================================================================
+ * Output side: cv::imwrite(result_name, result) with the default "result.jpg" (image_stitching.cpp:81, :1228; the timelapse
+ * frames of :1214 likewise).  OpenCV hands the image to libjpeg with its defaults - quality 95, YCbCr 4:2:0, baseline
+ * sequential DCT (JDCT_ISLOW), the Annex K Huffman tables, no restart markers, JFIF 1.01 - after converting a 16S result with
+ * saturate_cast<uchar>.  The whole pipeline is integer arithmetic; the device reproduces the file byte for byte.
+ * image: 8UC3 (is_16s = 0) or 16SC3 (is_16s = 1, what blend() returns), BGR, host or device pointer.
+ * out: host or device buffer of `capacity` bytes; *out_size receives the stream size.  If the buffer is too small (or NULL)
+ * the call returns ISB_ERR_OUT_OF_RANGE with *out_size = the size needed.  quality: 1..100 (imwrite's default: 95).
+ * Images beyond libjpeg's 65500-pixel limit per side are refused (ISB_ERR_OUT_OF_RANGE), as imwrite refuses them.
+ * ============================================================================================ */
+ISB_API int isb_jpeg_encode(const void* image, int width, int height, size_t pitch_bytes, int is_16s, int quality, uint8_t* out,
+                            size_t capacity, size_t* out_size);
+
 /* Peer-memory plumbing for the fused "collapse + gather" of the strip-sharded path: rank 0 allocates the panorama
  * with isb_device_malloc and exports it; the other ranks open the handle and pass the returned pointer as
  * isb_pano.data / .mask, so that the final blend kernel stores its rows straight into rank 0's HBM over NVLink. */
