@@ -461,6 +461,11 @@ def measure(name, div, args, rank, world, dev, stream, full):
         dist.barrier()
     res["parity"] = parity or None
     res["cpu_baseline"] = cpu
+    if rank == 0 and full and cpu is not None and world == 1 and max(pw, ph) <= 65500:
+        try:
+            res["output_side"] = measure_output_side(panos[0][0], panos[0][1], o8)
+        except Exception as e:  # noqa: BLE001  (a side record must not take the headline line down)
+            res["output_side"] = {"error": repr(e)}
 
     # ---- video-rate loop (BASELINE config 4): one synchronised call per frame -> latency percentiles ------------------
     if full and args.video > 0 and world == 1:
@@ -597,6 +602,34 @@ def measure_e2e(rig, imgs, gains, seams, cams, sizes, roi, args, rank, world, de
         barrier()
         shared.close()
     return r
+
+
+def measure_output_side(d_out, d_mask, o8):
+    """What follows blend() in the reference: imwrite(result_name, result) (image_stitching.cpp:1228) and the crop() of cropper.cpp
+    on the composited mask.  GPU: isb_jpeg_encode from the device-resident panorama to the file bytes in host memory, and
+    isb_crop_rect on the device-resident mask; CPU: cv2.imencode of the same panorama (libjpeg-turbo, what imwrite calls)."""
+    import cv2
+    import torch
+
+    import image_stitching_b200 as isb
+    ts = []
+    for _ in range(3):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        jpg = isb.imencode_jpg(d_out)
+        ts.append(time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    ok, ref = cv2.imencode(".jpg", o8)
+    t_cpu = time.perf_counter() - t0
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    rect = isb.crop_rect(d_mask)
+    t_crop = time.perf_counter() - t0
+    mp = o8.shape[0] * o8.shape[1] / 1e6
+    return {"imwrite_jpg": {"gpu_ms": min(ts) * 1e3, "gpu_MP_per_s": mp / min(ts), "cpu_ms": t_cpu * 1e3, "cpu_MP_per_s": mp / t_cpu,
+                            "bytes": len(jpg), "equal_to_cv2_imencode": bool(ok and jpg == ref.tobytes()),
+                            "note": "quality 95, 4:2:0, baseline - imwrite's defaults; GPU time includes the copy of the file bytes to host memory"},
+            "crop": {"rect_xywh": [int(v) for v in rect], "gpu_ms": t_crop * 1e3}}
 
 
 def measure_cfg1_substitute(args, dev, stream):
@@ -758,6 +791,8 @@ def run_ours(args, rank, world):
                             "data": "synthetic, generated on the device (same construction as the numpy rig)"}
         if cfg1 is not None:
             line["cfg1_substitute"] = cfg1
+        if res.get("output_side"):
+            line["output_side"] = res["output_side"]
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

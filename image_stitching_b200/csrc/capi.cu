@@ -443,6 +443,7 @@ int isb_jpeg_encode(const void* image, int w, int h, size_t pitch, int is_16s, i
 {
     return guarded([&] { jpeg_encode(image, w, h, pitch, is_16s, quality, out, capacity, out_size); });
 }
+int isb_jpeg_release_workspace(void) { return guarded([&] { jpeg_release_workspace(); }); }
 
 // ---- composer ---------------------------------------------------------------------------------------
 isb_composer* isb_composer_create(const isb_config* cfg)

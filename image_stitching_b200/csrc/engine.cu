@@ -77,6 +77,12 @@ DevBuf::~DevBuf()
 {
     if (p_) cudaFree(p_);
 }
+void DevBuf::release()
+{
+    if (p_) cudaFree(p_);
+    p_ = nullptr;
+    cap_ = 0;
+}
 void* DevBuf::ensure(size_t bytes)
 {
     if (bytes <= cap_ && p_) return p_;

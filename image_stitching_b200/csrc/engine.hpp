@@ -45,6 +45,7 @@ public:
     DevBuf& operator=(const DevBuf&) = delete;
     ~DevBuf();
     void* ensure(size_t bytes);
+    void release();  // frees the block (synchronises like cudaFree)
     template <typename T> T* as() const { return static_cast<T*>(p_); }
     size_t capacity() const { return cap_; }
 private:
@@ -196,6 +197,7 @@ void crop_rect_image(const void* img, int W, int H, size_t pitch, int is_16s, in
 
 // cv::imwrite("result.jpg", result) of the reference (image_stitching.cpp:1228) on the device: jpeg.cu
 void jpeg_encode(const void* image, int W, int H, size_t pitch, int is_16s, int quality, uint8_t* out, size_t capacity, size_t* out_size);
+void jpeg_release_workspace();  // frees the calling thread's cached work buffers of jpeg_encode
 
 void seam_mask_apply(const uint8_t* seam, int mw, int mh, size_t spitch, uint8_t* mask, int w, int h, size_t pitch);
 

@@ -491,7 +491,42 @@ std::vector<uint8_t> jpeg_header(int w, int h, const uint8_t ql[64], const uint8
     return o;
 }
 
+struct JpegWorkspace {
+    DevBuf b[11];
+    void* pinned = nullptr;  // host staging of the finished stream: a pageable destination is filled from here
+    size_t pinned_cap = 0;
+    uint8_t* host(size_t bytes)
+    {
+        if (bytes > pinned_cap) {
+            if (pinned) cudaFreeHost(pinned);
+            pinned = nullptr;
+            pinned_cap = 0;
+            ISB_CUDA(cudaHostAlloc(&pinned, bytes + bytes / 4, cudaHostAllocDefault));
+            pinned_cap = bytes + bytes / 4;
+        }
+        return static_cast<uint8_t*>(pinned);
+    }
+    void release()
+    {
+        for (DevBuf& d : b) d.release();
+        if (pinned) cudaFreeHost(pinned);
+        pinned = nullptr;
+        pinned_cap = 0;
+    }
+    ~JpegWorkspace() { if (pinned) cudaFreeHost(pinned); }
+};
+JpegWorkspace& workspace()
+{
+    static thread_local JpegWorkspace ws;
+    return ws;
+}
+
 }  // namespace
+
+void jpeg_release_workspace()
+{
+    workspace().release();
+}
 
 void jpeg_encode(const void* image, int W, int H, size_t pitch, int is_16s, int quality, uint8_t* out, size_t capacity, size_t* out_size)
 {
@@ -521,7 +556,11 @@ void jpeg_encode(const void* image, int W, int H, size_t pitch, int is_16s, int 
     derive(kAcChromaBits, kAcChromaVals, tb.ac[1]);
     const std::vector<uint8_t> hdr = jpeg_header(W, H, ql, qc);
 
-    DevBuf ibuf, planes, tbuf, cbuf, bbuf, obuf, pbuf, wbuf, fbuf, fobuf, dout;
+    // grow-only work buffers, kept per calling thread between calls (an encode of a 60 MP panorama needs ~ 0.4 GB of them, and
+    // allocating and freeing that much costs more than the kernels); isb_jpeg_release_workspace() gives them back
+    JpegWorkspace& ws = workspace();
+    DevBuf &ibuf = ws.b[0], &planes = ws.b[1], &tbuf = ws.b[2], &cbuf = ws.b[3], &bbuf = ws.b[4], &obuf = ws.b[5], &pbuf = ws.b[6], &wbuf = ws.b[7],
+           &fbuf = ws.b[8], &fobuf = ws.b[9], &dout = ws.b[10];
     const void* d = image;
     size_t dp = pitch;
     if (mem_kind(image) != MemKind::Device) {
@@ -582,8 +621,13 @@ void jpeg_encode(const void* image, int W, int H, size_t pitch, int is_16s, int 
     count_launch();
     const uint8_t eoi[2] = {0xFF, 0xD9};
     ISB_CUDA(cudaMemcpyAsync(dst + hdr.size() + body, eoi, 2, cudaMemcpyHostToDevice, st));
-    if (!odev) ISB_CUDA(cudaMemcpyAsync(out, dst, total, cudaMemcpyDeviceToHost, st));
-    ISB_CUDA(cudaStreamSynchronize(st));  // hdr / eoi are locals; the staging buffers are released on return
+    uint8_t* hp = nullptr;
+    if (!odev) {
+        hp = mem_kind(out) == MemKind::HostPinned ? out : ws.host(total);
+        ISB_CUDA(cudaMemcpyAsync(hp, dst, total, cudaMemcpyDeviceToHost, st));
+    }
+    ISB_CUDA(cudaStreamSynchronize(st));  // hdr / eoi are locals
+    if (hp && hp != out) std::memcpy(out, hp, total);
     ISB_CUDA(cudaGetLastError());
 }
 

@@ -365,6 +365,8 @@ ISB_API int isb_crop_rect_image(const void* image, int width, int height, size_t
  * ============================================================================================ */
 ISB_API int isb_jpeg_encode(const void* image, int width, int height, size_t pitch_bytes, int is_16s, int quality, uint8_t* out,
                             size_t capacity, size_t* out_size);
+/* The encoder keeps its device work buffers (about 7 bytes per pixel) per calling thread between calls; this frees them. */
+ISB_API int isb_jpeg_release_workspace(void);
 
 /* Peer-memory plumbing for the fused "collapse + gather" of the strip-sharded path: rank 0 allocates the panorama
  * with isb_device_malloc and exports it; the other ranks open the handle and pass the returned pointer as
