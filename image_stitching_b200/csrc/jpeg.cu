@@ -518,6 +518,17 @@ struct JpegWorkspace {
 JpegWorkspace& workspace()
 {
     static thread_local JpegWorkspace ws;
+    static thread_local int ws_device = -1;
+    int dev = -1;
+    cudaGetDevice(&dev);
+    if (dev != ws_device) {  // the blocks belong to the device they were allocated on
+        if (ws_device >= 0) {
+            cudaSetDevice(ws_device);
+            ws.release();
+            cudaSetDevice(dev);
+        }
+        ws_device = dev;
+    }
     return ws;
 }
 
