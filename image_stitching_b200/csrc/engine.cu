@@ -468,6 +468,12 @@ void PyramidEngine::blend(const OutDev& out, cudaStream_t st)
                         if (may_weigh(list[e], c % dst_.cells_x, c / dst_.cells_x, 0)) desc0.push_back(desc[e]);  // level-0 record
                 }
                 start0[ncell] = (int)desc0.size();
+                if (getenv("ISB_DEBUG_PLAN")) {
+                    long long covered = 0;
+                    for (int c = 0; c < ncell; ++c) covered += start0[c + 1] > start0[c];
+                    fprintf(stderr, "[isb plan] blend lists: %d cells (%lld covered), %d entries, %zu after the occupancy filter (%.2f per covered cell)\n",
+                            ncell, covered, dst_.n_entries, desc0.size(), covered ? (double)desc0.size() / covered : 0.0);
+                }
                 int* s0 = static_cast<int*>(cells0_dev_.ensure(start0.size() * sizeof(int)));
                 CellTile* d0 = static_cast<CellTile*>(cdesc0_dev_.ensure(std::max<size_t>(desc0.size(), 1) * sizeof(CellTile)));
                 ISB_CUDA(cudaMemcpyAsync(s0, start0.data(), start0.size() * sizeof(int), cudaMemcpyHostToDevice, st));
