@@ -17,6 +17,9 @@ is cfg2: 8 x 4000x3000 images, spherical warp, 5 bands, 20912x2881 panorama.
            (default, overlaps the next step), by peer stores from the final kernel (--gather p2p) or by NCCL (--gather
            nccl).  scaling = "strong".  Every line carries `parity` (gathered panorama vs the unsharded result computed on
            rank 0, and vs cv2) and a `cfg3` sub-record (the 36 x 24 MP rig the north star names for strip scaling).
+  output_side (N = 1): what follows blend() in the reference - imwrite("result.jpg", result) (:1228) and cropper.cpp's crop():
+           the JPEG file of the full-size panorama from isb_jpeg_encode, compared byte for byte with cv2.imencode and timed
+           against it, and the crop rectangle of the composited mask.
   --impl reference : the reference's own CPU implementation of the path (OpenCV's cv::detail classes, driven through cv2
            in the reference's call order) on the host cores, all images of the rig per step; rank 0 only.
 """
