@@ -20,6 +20,8 @@ is cfg2: 8 x 4000x3000 images, spherical warp, 5 bands, 20912x2881 panorama.
   output_side (N = 1): what follows blend() in the reference - imwrite("result.jpg", result) (:1228) and cropper.cpp's crop():
            the JPEG file of the full-size panorama from isb_jpeg_encode, compared byte for byte with cv2.imencode and timed
            against it, and the crop rectangle of the composited mask.
+  e2e_to_jpeg (N = 1): decoded frames in pinned host memory -> result.jpg bytes in pinned host memory (compose + encode on
+           the device, `--e2e-depth` host threads with one composer / stream each); the file is compared with cv2.imencode's.
   --impl reference : the reference's own CPU implementation of the path (OpenCV's cv::detail classes, driven through cv2
            in the reference's call order) on the host cores, all images of the rig per step; rank 0 only.
 """
@@ -494,6 +496,11 @@ def measure(name, div, args, rank, world, dev, stream, full):
     # ---- e2e: pinned host buffers through the C ABI -------------------------------------------------------------------
     if full and not args.no_e2e:
         res["e2e"] = measure_e2e(rig, imgs, gains, seams, cams, sizes, roi, args, rank, world, dev, stream, o8, om, barrier)
+        if world == 1 and o8 is not None and max(roi[2], roi[3]) <= 65500 and not args.no_cpu_baseline:
+            try:
+                res["e2e_to_jpeg"] = measure_e2e_to_jpeg(rig, imgs, gains, seams, cams, sizes, roi, args, dev, stream, o8)
+            except Exception as e:  # noqa: BLE001  (a side record must not take the headline line down)
+                res["e2e_to_jpeg"] = {"error": repr(e)}
     del d_imgs, panos
     return res
 
@@ -605,6 +612,99 @@ def measure_e2e(rig, imgs, gains, seams, cams, sizes, roi, args, rank, world, de
     if shared is not None:
         barrier()
         shared.close()
+    return r
+
+
+def measure_e2e_to_jpeg(rig, imgs, gains, seams, cams, sizes, roi, args, dev, stream, o8_ref):
+    """The reference's whole deliverable, frames in -> result.jpg out (image_stitching.cpp:1086-1229 incl. the imwrite of :1228),
+    end to end on one GPU: every step uploads the decoded frames from pinned host memory, composes the panorama on the device,
+    encodes it there (isb_jpeg_encode) and downloads the FILE (tens of MB) instead of the raw panorama (241 MB for cfg2).  The
+    encoder returns when its file is in host memory, so `depth` host threads - one composer, stream and output slot each - keep
+    the PCIe link busy the way the pipelined composers of `e2e` do."""
+    import ctypes as C
+    import threading as th
+
+    import cv2
+    import torch
+
+    import image_stitching_b200 as isb
+    pw, ph = roi[2], roi[3]
+    depth = max(1, args.e2e_depth)
+    steps = max(depth, min(args.steps, 50))
+    h_imgs = [torch.from_numpy(im).pin_memory().numpy() for im in imgs]
+    h_gains = [torch.from_numpy(g).pin_memory().numpy() for g in gains]
+    h_seams = [torch.from_numpy(s_).pin_memory().numpy() for s_ in seams]
+    cap = pw * ph
+    slots = []
+    for _ in range(depth):
+        c = isb.Composer(rig.warp, rig.scale, rig.nb, cache_plan=True, async_mode=True)
+        c.plan(cams, sizes)
+        slots.append(dict(comp=c, stream=torch.cuda.Stream(device=dev), d8=torch.zeros((ph, pw, 3), dtype=torch.uint8, device=dev),
+                          dm=torch.zeros((ph, pw), dtype=torch.uint8, device=dev), file=torch.zeros(cap, dtype=torch.uint8).pin_memory(),
+                          n=C.c_size_t(0), err=None))
+    L = isb.lib()
+
+    # persistent workers (the encoder's work buffers live per thread): phases = warm-up, run 1, run 2
+    phases = [2 * depth, steps, steps]
+    gate = th.Barrier(depth + 1)
+
+    def worker(k):
+        sl = slots[k]
+        torch.cuda.set_device(dev)
+        isb.set_stream(sl["stream"].cuda_stream)
+        for n_total in phases:
+            n_steps = n_total // depth + (1 if k < n_total % depth else 0)
+            gate.wait()  # start of the phase
+            try:
+                for _ in range(n_steps if not sl["err"] else 0):
+                    sl["comp"].run(h_imgs, h_gains, h_seams, out=sl["d8"], out_mask=sl["dm"])
+                    rc = L.isb_jpeg_encode(C.c_void_p(sl["d8"].data_ptr()), pw, ph, C.c_size_t(pw * 3), 0, 95, C.c_void_p(sl["file"].data_ptr()),
+                                           C.c_size_t(cap), C.byref(sl["n"]))
+                    if rc != 0:
+                        raise RuntimeError(f"isb_jpeg_encode failed ({rc})")
+            except Exception as e:  # noqa: BLE001
+                sl["err"] = repr(e)
+            gate.wait()  # end of the phase
+
+    ts = [th.Thread(target=worker, args=(k,)) for k in range(depth)]
+    for t in ts:
+        t.start()
+
+    def loop():
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for sl in slots:
+            sl["stream"].wait_event(e0)
+        t0 = time.perf_counter()
+        gate.wait()
+        gate.wait()
+        wall = (time.perf_counter() - t0) * 1e3
+        for sl in slots:
+            stream.wait_stream(sl["stream"])
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return max(e0.elapsed_time(e1), wall)  # the files are in host memory when the workers return: the later clock counts
+
+    loop()
+    runs = [loop() for _ in range(2)]
+    for t in ts:
+        t.join()
+    for sl in slots:
+        if sl["err"]:
+            raise RuntimeError(sl["err"])
+    ms = min(runs) / steps
+    ok, ref = cv2.imencode(".jpg", o8_ref)
+    refb = ref.tobytes()
+    equal = bool(ok and all(sl["file"][: sl["n"].value].numpy().tobytes() == refb for sl in slots))
+    isb.set_stream(stream.cuda_stream)
+    out_mp = pw * ph / 1e6
+    h2d = slots[0]["comp"].last_h2d_bytes() + sum(g.nbytes for g in gains) + sum(s_.nbytes for s_ in seams)
+    r = {"value": out_mp / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "steps": steps, "runs_ms_per_step": [m / steps for m in runs],
+         "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(slots[0]["n"].value), "host_threads": depth,
+         "file_equals_cv2_imencode_of_the_panorama": equal,
+         "what": "decoded frames in pinned host memory -> result.jpg bytes in pinned host memory (compose + imwrite's JPEG encoding on the device)"}
+    del slots
     return r
 
 
@@ -798,6 +898,8 @@ def run_ours(args, rank, world):
             line["cfg1_substitute"] = cfg1
         if res.get("output_side"):
             line["output_side"] = res["output_side"]
+        if res.get("e2e_to_jpeg"):
+            line["e2e_to_jpeg"] = res["e2e_to_jpeg"]
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -493,6 +493,8 @@ std::vector<uint8_t> jpeg_header(int w, int h, const uint8_t ql[64], const uint8
 
 struct JpegWorkspace {
     DevBuf b[11];
+    int tables_quality = -1;  // quality whose tables b[2] holds (uploaded once: an upload per call would queue behind whatever
+                              // large host -> device copy another stream has in flight on the copy engine)
     void* pinned = nullptr;  // host staging of the finished stream: a pageable destination is filled from here
     size_t pinned_cap = 0;
     uint8_t* host(size_t bytes)
@@ -509,6 +511,7 @@ struct JpegWorkspace {
     void release()
     {
         for (DevBuf& d : b) d.release();
+        tables_quality = -1;
         if (pinned) cudaFreeHost(pinned);
         pinned = nullptr;
         pinned_cap = 0;
@@ -585,7 +588,12 @@ void jpeg_encode(const void* image, int W, int H, size_t pitch, int is_16s, int 
     uint8_t* Cbp = Yp + ysz;
     uint8_t* Crp = Cbp + csz;
     JpegTables* td = static_cast<JpegTables*>(tbuf.ensure(sizeof(JpegTables)));
-    ISB_CUDA(cudaMemcpyAsync(td, &tb, sizeof(tb), cudaMemcpyHostToDevice, st));
+    const int qkey = std::min(std::max(quality, 1), 100);
+    if (ws.tables_quality != qkey) {
+        ISB_CUDA(cudaMemcpyAsync(td, &tb, sizeof(tb), cudaMemcpyHostToDevice, st));
+        ISB_CUDA(cudaStreamSynchronize(st));  // `tb` is a local
+        ws.tables_quality = qkey;
+    }
     {
         const dim3 grid((G.pw / 2 + 31) / 32, (G.ph / 2 + 7) / 8);
         if (is_16s) jpeg_planes_kernel<int16_t><<<grid, 256, 0, st>>>(static_cast<const int16_t*>(d), (long long)dp, W, H, G.pw, G.ph, Yp, Cbp, Crp);
@@ -626,19 +634,26 @@ void jpeg_encode(const void* image, int W, int H, size_t pitch, int is_16s, int 
     *out_size = total;
     if (!out || capacity < total) throw Error(ISB_ERR_OUT_OF_RANGE, "jpeg: the output buffer is smaller than the stream (out_size holds the size needed)");
     const bool odev = mem_kind(out) == MemKind::Device;
-    uint8_t* dst = odev ? out : static_cast<uint8_t*>(dout.ensure(total));
-    ISB_CUDA(cudaMemcpyAsync(dst, hdr.data(), hdr.size(), cudaMemcpyHostToDevice, st));
-    jpeg_stuff_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, st>>>(words, n_words, n_bytes, ffo, dst + hdr.size());
-    count_launch();
     const uint8_t eoi[2] = {0xFF, 0xD9};
-    ISB_CUDA(cudaMemcpyAsync(dst + hdr.size() + body, eoi, 2, cudaMemcpyHostToDevice, st));
-    uint8_t* hp = nullptr;
-    if (!odev) {
-        hp = mem_kind(out) == MemKind::HostPinned ? out : ws.host(total);
-        ISB_CUDA(cudaMemcpyAsync(hp, dst, total, cudaMemcpyDeviceToHost, st));
+    if (odev) {
+        ISB_CUDA(cudaMemcpyAsync(out, hdr.data(), hdr.size(), cudaMemcpyHostToDevice, st));
+        jpeg_stuff_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, st>>>(words, n_words, n_bytes, ffo, out + hdr.size());
+        count_launch();
+        ISB_CUDA(cudaMemcpyAsync(out + hdr.size() + body, eoi, 2, cudaMemcpyHostToDevice, st));
+        ISB_CUDA(cudaStreamSynchronize(st));  // hdr / eoi are locals
+    } else {
+        // host destination: only the entropy-coded body crosses the bus; the header and the EOI marker are written by the host
+        // (no host -> device copy at all: it would wait on the copy engine behind other streams' uploads)
+        uint8_t* dbody = static_cast<uint8_t*>(dout.ensure(body));
+        jpeg_stuff_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, st>>>(words, n_words, n_bytes, ffo, dbody);
+        count_launch();
+        uint8_t* hp = mem_kind(out) == MemKind::HostPinned ? out + hdr.size() : ws.host(body);
+        ISB_CUDA(cudaMemcpyAsync(hp, dbody, body, cudaMemcpyDeviceToHost, st));
+        std::memcpy(out, hdr.data(), hdr.size());
+        ISB_CUDA(cudaStreamSynchronize(st));
+        if (hp != out + hdr.size()) std::memcpy(out + hdr.size(), hp, body);
+        std::memcpy(out + hdr.size() + body, eoi, 2);
     }
-    ISB_CUDA(cudaStreamSynchronize(st));  // hdr / eoi are locals
-    if (hp && hp != out) std::memcpy(out, hp, total);
     ISB_CUDA(cudaGetLastError());
 }
 
