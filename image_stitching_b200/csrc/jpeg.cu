@@ -615,15 +615,17 @@ void jpeg_encode(const void* image, int W, int H, size_t pitch, int is_16s, int 
     ISB_CUDA(cudaMemcpyAsync(&total_bits, part + np, 8, cudaMemcpyDeviceToHost, st));
     ISB_CUDA(cudaStreamSynchronize(st));
     const long long n_bytes = (long long)((total_bits + 7) / 8), n_words = (n_bytes + 3) / 4;
-    uint32_t* words = static_cast<uint32_t*>(wbuf.ensure((size_t)(n_words + 1) * 4));
+    // (the data-dependent buffers are requested with a quarter of headroom: a video's next frame is rarely larger than that)
+    const size_t room = (size_t)n_words + (size_t)n_words / 4 + 16;
+    uint32_t* words = static_cast<uint32_t*>(wbuf.ensure(room * 4));
     ISB_CUDA(cudaMemsetAsync(words, 0, (size_t)(n_words + 1) * 4, st));
     jpeg_emit_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, coef, td, offs, bits, words);
     count_launch();
     // byte stuffing: count, scan, scatter
-    uint32_t* ffc = static_cast<uint32_t*>(fbuf.ensure((size_t)n_words * 4));
-    unsigned long long* ffo = static_cast<unsigned long long*>(fobuf.ensure((size_t)n_words * 8));
+    uint32_t* ffc = static_cast<uint32_t*>(fbuf.ensure(room * 4));
+    unsigned long long* ffo = static_cast<unsigned long long*>(fobuf.ensure(room * 8));
     const long long npw = (n_words + kScanBlock - 1) / kScanBlock;
-    unsigned long long* partw = static_cast<unsigned long long*>(pbuf.ensure((size_t)(std::max(np, npw) + 1) * 8));
+    unsigned long long* partw = static_cast<unsigned long long*>(pbuf.ensure((size_t)(std::max(np, npw) + npw / 4 + 2) * 8));
     jpeg_ff_count_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, st>>>(words, n_words, n_bytes, ffc);
     count_launch();
     exclusive_scan(ffc, n_words, ffo, partw, st);
@@ -644,7 +646,7 @@ void jpeg_encode(const void* image, int W, int H, size_t pitch, int is_16s, int 
     } else {
         // host destination: only the entropy-coded body crosses the bus; the header and the EOI marker are written by the host
         // (no host -> device copy at all: it would wait on the copy engine behind other streams' uploads)
-        uint8_t* dbody = static_cast<uint8_t*>(dout.ensure(body));
+        uint8_t* dbody = static_cast<uint8_t*>(dout.ensure(body + body / 4));
         jpeg_stuff_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, st>>>(words, n_words, n_bytes, ffo, dbody);
         count_launch();
         uint8_t* hp = mem_kind(out) == MemKind::HostPinned ? out + hdr.size() : ws.host(body);
